@@ -1,0 +1,638 @@
+// engine.cu -- sm_100a kernels, host-side engine and the C ABI of libtwb200.so.
+//
+// Kernels (all hand-written, one thread per logical process, HBM-bound integer/f64 work):
+//   k_step<M>     one super-step of every LP of this partition (tw_core.cuh::lp_step), followed by the
+//                 in-kernel GVT reduction: warp shuffle min -> one atomicMin per block -> the last block
+//                 publishes GVT (Samadi's round trip through the Time Server,
+//                 Simulation/Aivika/Distributed/Optimistic/Internal/TimeServer.hs:369-421, collapses into this)
+//   k_route<M>    host-injected messages (enqueueMessage from runEventInStartTime / QueueMessageBulk) -> inboxes
+//   k_init<M>     newEventQueue for every LP (Internal/Event.hs:92-116)
+//   k_collect<M>  committed-event count and trace-hash sum
+// Multi-GPU: LP ranges are sharded (LP i lives on rank i / n_per); remote sends are direct NVLink peer
+// stores + peer atomics issued from inside k_step (no staging, no separate exchange kernel), and GVT is an
+// ncclAllReduce(min) of one double between steps.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "tw_core.cuh"
+
+namespace twb {
+
+constexpr int kBlock = 128;
+static std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------ device helpers
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+
+enum { C_EXEC = 0, C_RB, C_ROLLBACKS, C_STRAG, C_ANTI, C_ANNIH, C_RETRY, C_SLOCAL, C_SREMOTE, C_FOSSIL, C_COUNT };
+
+// Block-level reduction of the per-thread accumulators, then the "last block" publishes GVT.
+__device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t step, uint32_t world, bool advance)
+{
+    __shared__ unsigned long long s_pend[kBlock / 32], s_emit[kBlock / 32];
+    __shared__ unsigned int s_cnt[C_COUNT];
+    __shared__ unsigned int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < C_COUNT) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long p = warp_min_u64(ordered_bits(acc.pend_min));
+    unsigned long long e = warp_min_u64(ordered_bits(acc.emit_min));
+    const uint32_t vals[C_COUNT] = {acc.exec, acc.rb_events, acc.rollbacks, acc.strag, acc.anti, acc.annih,
+                                    acc.retry, acc.sent_local, acc.sent_remote, acc.fossil};
+#pragma unroll
+    for (int i = 0; i < C_COUNT; ++i) {
+        const unsigned int s = __reduce_add_sync(0xffffffffu, vals[i]);
+        if (lane == 0 && s) atomicAdd(&s_cnt[i], s);
+    }
+    if (acc.err) { if (atomicCAS(&ctl->error, 0u, acc.err) == 0u) ctl->err_lp = acc.err_lp; }
+    if (lane == 0) { s_pend[warp] = p; s_emit[warp] = e; }
+    __syncthreads();
+    if (threadIdx.x < C_COUNT) {
+        const unsigned int s = s_cnt[threadIdx.x];
+        if (s) atomicAdd(&ctl->c_exec + threadIdx.x, (unsigned long long)s);
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kBlock / 32; ++w) { p = s_pend[w] < p ? s_pend[w] : p; e = s_emit[w] < e ? s_emit[w] : e; }
+        if (p != ordered_bits(pos_inf())) atomicMin(&ctl->pend_min, p);
+        if (e != ordered_bits(pos_inf())) atomicMin(&ctl->emit_min, e);
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&ctl->done_blocks, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long pm = *(volatile unsigned long long *)&ctl->pend_min;
+        const unsigned long long em = *(volatile unsigned long long *)&ctl->emit_min;
+        const double g = from_ordered(pm < em ? pm : em);
+        ctl->gvt_local = g;
+        if (world == 1) ctl->gvt = g;            // otherwise ncclAllReduce(min) gvt_local -> gvt follows on the stream
+        ctl->pend_min = ordered_bits(pos_inf());
+        ctl->emit_min = ordered_bits(pos_inf());
+        if (advance) { ctl->step = step + 1; ctl->c_steps += 1; }
+        ctl->done_blocks = 0;
+        __threadfence();
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_step(const Dev<M> d)
+{
+    Ctl *ctl = d.ctl;
+    const double gvt = *(volatile double *)&ctl->gvt;
+    if (*(volatile uint32_t *)&ctl->error) return;
+    if (!(gvt <= d.stop)) return;                 // GVT passed the stop time: the run is complete
+    const uint32_t step = *(volatile uint32_t *)&ctl->step;
+    double wend = d.stop;
+    if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
+    Acc acc; acc.init();
+    const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
+    if (l < d.n_local) lp_step<M>(d, acc, l, gvt, wend, step & 1u);
+    if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
+    block_finish(ctl, acc, step, d.world, true);
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_route(const Dev<M> d, const tw_event *evs, size_t n)
+{
+    Ctl *ctl = d.ctl;
+    const uint32_t step = ctl->step;
+    const double gvt = ctl->gvt;
+    Acc acc; acc.init();
+    for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
+        const tw_event w = evs[i];
+        if (w.recv_ts < gvt) { acc.fail(TW_ERR_OUTDATED_MESSAGE, w.dst); continue; }
+        route_event<M>(d, acc, (step & 1u) ^ 1u, w);
+    }
+    // fold the injected minimum into GVT: gvt = min(gvt, min recv_ts)
+    __shared__ unsigned long long s_emit[kBlock / 32];
+    unsigned long long e = warp_min_u64(ordered_bits(acc.emit_min));
+    if ((threadIdx.x & 31) == 0) s_emit[threadIdx.x >> 5] = e;
+    if (acc.err) { if (atomicCAS(&ctl->error, 0u, acc.err) == 0u) ctl->err_lp = acc.err_lp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kBlock / 32; ++w) e = s_emit[w] < e ? s_emit[w] : e;
+        if (e != ordered_bits(pos_inf())) atomicMin(&ctl->emit_min, e);
+    }
+}
+
+// after k_route: gvt = min(gvt, injected minimum)   (single thread)
+__global__ void k_fold_inject(Ctl *ctl)
+{
+    const double m = from_ordered(ctl->emit_min);
+    if (m < ctl->gvt) ctl->gvt = m;
+    if (m < ctl->gvt_local) ctl->gvt_local = m;
+    ctl->emit_min = ordered_bits(pos_inf());
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_time)
+{
+    const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
+    if (l == 0) {
+        Ctl c; memset(&c, 0, sizeof c);
+        c.gvt = start_time; c.gvt_local = start_time;
+        c.pend_min = ordered_bits(pos_inf()); c.emit_min = ordered_bits(pos_inf());
+        *d.ctl = c;
+    }
+    if (l >= d.n_local) return;
+    LPHdr h; h.head = 0; h.nproc = 0; h.consumed = 0; h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
+    d.hdr[l] = h;
+    LPIn in; in.total = 0; in.cnt[0] = 0; in.cnt[1] = 0; in.pad = 0;
+    d.in[l] = in;
+    d.state[l] = M::initial_state(d.mp, d.lp_base + l);
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_collect(const Dev<M> d, unsigned long long *out /* [2] */)
+{
+    unsigned long long n = 0, hsum = 0;
+    for (uint32_t l = blockIdx.x * kBlock + threadIdx.x; l < d.n_local; l += gridDim.x * kBlock) {
+        n += d.state[l].n_exec; hsum += d.state[l].hash;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); hsum += __shfl_xor_sync(0xffffffffu, hsum, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], n); atomicAdd(&out[1], hsum); }
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_gather_stats(const Dev<M> d, unsigned long long *n_exec, unsigned long long *hash)
+{
+    const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
+    if (l >= d.n_local) return;
+    n_exec[l] = d.state[l].n_exec; hash[l] = d.state[l].hash;
+}
+
+__global__ void k_gather_machrep(const Dev<MachRepModel> d, tw_machrep_result *out, uint32_t n_rep, double t_stop)
+{
+    const uint32_t r = blockIdx.x * kBlock + threadIdx.x;
+    if (r >= n_rep) return;
+    // masters owned by this partition, in order
+    const uint32_t first_master = ((d.lp_base + 2u) / 3u) * 3u;
+    const uint32_t lp = first_master + 3u * r;
+    if (lp < d.lp_base || lp >= d.lp_base + d.n_local) return;
+    const MachRepModel::State s = d.state[lp - d.lp_base];
+    tw_machrep_result o;
+    o.total_up_time = s.total_up_time; o.n_rep = s.n_rep; o.n_immed_rep = s.n_immed;
+    o.up_time_prop = s.total_up_time / (2.0 * t_stop);              // tests/MachRep2DistributedReproducible.hs:214-217
+    o.immed_prop = (double)s.n_immed / (double)s.n_rep;              // :219-224
+    out[r] = o;
+}
+
+// ------------------------------------------------------------------ NCCL through dlopen (torch-bundled or system libnccl.so.2)
+
+struct NcclId128 { char b[128]; };      // ncclUniqueId is passed by value
+struct NcclApi {
+    typedef NcclId128 Id128;
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId128, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load(std::string &err)
+    {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define TW_SYM(field, name) *(void **)(&field) = dlsym(lib, name); if (!field) { err = std::string("missing NCCL symbol ") + name; return false; }
+        TW_SYM(GetUniqueId, "ncclGetUniqueId");
+        TW_SYM(CommInitRank, "ncclCommInitRank");
+        TW_SYM(CommDestroy, "ncclCommDestroy");
+        TW_SYM(AllReduce, "ncclAllReduce");
+        TW_SYM(AllGather, "ncclAllGather");
+        TW_SYM(GetErrorString, "ncclGetErrorString");
+#undef TW_SYM
+        return true;
+    }
+};
+static NcclApi g_nccl;
+enum { kNcclInt8 = 0, kNcclFloat64 = 8, kNcclMin = 3 };   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+// ------------------------------------------------------------------ host engine
+
+struct EngineBase {
+    std::string err;
+    virtual ~EngineBase() {}
+    virtual int reset() = 0;
+    virtual int enqueue(const tw_event *evs, size_t n) = 0;
+    virtual int run(double until, tw_run_stats *st) = 0;
+    virtual int gvt(double *g) = 0;
+    virtual int lp_state(uint32_t lp, tw_lp_state *out) = 0;
+    virtual int read_lp_stats(uint64_t *n_exec, uint64_t *hash, size_t n) = 0;
+    virtual int read_machrep(tw_machrep_result *out, size_t n) = 0;
+    virtual void partition(uint32_t *base, uint32_t *n) const = 0;
+};
+
+#define TW_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            char _b[512]; snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            err = _b; return TW_ERR_CUDA;                                                               \
+        }                                                                                               \
+    } while (0)
+#define TW_NCCL(call)                                                                                   \
+    do {                                                                                                \
+        int _e = (call);                                                                                \
+        if (_e != 0) {                                                                                  \
+            char _b[512]; snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(_e), __FILE__, __LINE__); \
+            err = _b; return TW_ERR_CUDA;                                                               \
+        }                                                                                               \
+    } while (0)
+
+static const char *code_name(int c)
+{
+    switch (c) {
+    case TW_OK: return "ok";
+    case TW_ERR_INVALID_ARG: return "invalid argument";
+    case TW_ERR_CUDA: return "CUDA/NCCL error or no usable sm_100 device";
+    case TW_ERR_SEND_AFTER_RECV: return "The Send time cannot be greater than the Receive message time";
+    case TW_ERR_OUTDATED_MESSAGE: return "Received the outdated message (receive time < GVT)";
+    case TW_ERR_QUEUE_OVERFLOW: return "per-LP queue capacity exceeded (event overflow)";
+    case TW_ERR_ANTI_UNMATCHED: return "Cannot annihilate another message (anti-message without twin)";
+    case TW_ERR_DEADLOCK: return "Detected a deadlock when retrying the computations (GVT stalled)";
+    case TW_ERR_TIME_ORDER: return "The time value is too small (pending event older than the LP clock)";
+    case TW_ERR_BAD_DESTINATION: return "receiver id outside [0, n_lps)";
+    case TW_ERR_MODEL: return "model handler reached an impossible state";
+    case TW_ERR_OUTBOX_OVERFLOW: return "cross-GPU staging buffer full";
+    case TW_ERR_NOT_SUPPORTED: return "not supported";
+    default: return "unknown error";
+    }
+}
+
+template <class M>
+struct Engine : EngineBase {
+    tw_params P;
+    Dev<M> d;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chk[2] = {nullptr, nullptr};
+    Ctl *h_ctl = nullptr;                 // pinned, 2 slots
+    tw_event *d_stage = nullptr; size_t stage_cap = 0;
+    unsigned long long *d_tmp = nullptr;  // [2]
+    cudaGraphExec_t graph = nullptr;
+    uint32_t graph_steps = 0;
+    void *comm = nullptr;                 // ncclComm_t
+    std::vector<void *> peer_ptrs;        // opened IPC mappings
+    uint64_t launches = 0;
+    int grid = 0;
+
+    int init(const tw_params &p)
+    {
+        P = p;
+        if (p.n_lps == 0 || p.world == 0 || p.world > (uint32_t)kMaxWorld || p.rank >= p.world) { err = "bad n_lps/rank/world"; return TW_ERR_INVALID_ARG; }
+        uint32_t cap = p.queue_capacity ? p.queue_capacity : 128;
+        if (cap & (cap - 1)) { err = "queue_capacity must be a power of two"; return TW_ERR_INVALID_ARG; }
+        if (cap < 8) { err = "queue_capacity must be >= 8"; return TW_ERR_INVALID_ARG; }
+        uint32_t mb = p.max_events_per_step ? p.max_events_per_step : kMaxBatch;
+        if (mb > (uint32_t)kMaxBatch) mb = kMaxBatch;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { err = "no CUDA device: the engine has no CPU fallback"; return TW_ERR_CUDA; }
+        if (p.device >= 0) TW_CUDA(cudaSetDevice(p.device));
+        int dev = 0; TW_CUDA(cudaGetDevice(&dev));
+        cudaDeviceProp prop; TW_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10) { char b[128]; snprintf(b, sizeof b, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor); err = b; return TW_ERR_CUDA; }
+        memset(&d, 0, sizeof d);
+        d.n_global = p.n_lps; d.world = p.world; d.rank = p.rank;
+        d.n_per = (p.n_lps + p.world - 1) / p.world;
+        if (std::is_same<M, MachRepModel>::value && p.world > 1) d.n_per = ((d.n_per + 2) / 3) * 3;   // keep replicas whole
+        d.lp_base = d.n_per * p.rank;
+        d.n_local = d.lp_base >= p.n_lps ? 0 : (p.n_lps - d.lp_base < d.n_per ? p.n_lps - d.lp_base : d.n_per);
+        d.cap = cap; d.mask = cap - 1; d.max_batch = mb;
+        d.proc_limit = p.proc_limit ? p.proc_limit : cap / 4;
+        d.fossil_thresh = p.fossil_threshold ? p.fossil_threshold : cap / 8;
+        d.stop = p.stop_time;
+        d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
+        d.mp = M::make_params(p);
+        const size_t nl = d.n_local ? d.n_local : 1;
+        TW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        TW_CUDA(cudaEventCreate(&ev0)); TW_CUDA(cudaEventCreate(&ev1));
+        TW_CUDA(cudaEventCreateWithFlags(&ev_chk[0], cudaEventDisableTiming));
+        TW_CUDA(cudaEventCreateWithFlags(&ev_chk[1], cudaEventDisableTiming));
+        TW_CUDA(cudaMalloc(&d.pages, nl * cap * sizeof(typename M::Event)));
+        TW_CUDA(cudaMalloc(&d.saved, nl * cap * sizeof(typename M::State)));
+        TW_CUDA(cudaMalloc(&d.state, nl * sizeof(typename M::State)));
+        TW_CUDA(cudaMalloc(&d.hdr, nl * sizeof(LPHdr)));
+        TW_CUDA(cudaMalloc(&d.in, nl * sizeof(LPIn)));
+        TW_CUDA(cudaMalloc(&d.ctl, sizeof(Ctl)));
+        TW_CUDA(cudaMalloc(&d_tmp, 2 * sizeof(unsigned long long)));
+        TW_CUDA(cudaHostAlloc(&h_ctl, 2 * sizeof(Ctl), cudaHostAllocDefault));
+        grid = (int)((nl + kBlock - 1) / kBlock);
+        d.peer_pages[d.rank] = d.pages; d.peer_in[d.rank] = d.in;
+        if (p.world > 1) { int rc = init_peers(); if (rc) return rc; }
+        return reset();
+    }
+
+    // exchange cudaIpc handles of pages / inbox counters through NCCL and map every peer (NVLink P2P)
+    int init_peers()
+    {
+        if (!g_nccl.load(err)) return TW_ERR_CUDA;
+        NcclApi::Id128 id; memcpy(id.b, P.nccl_id, 128);
+        TW_NCCL(g_nccl.CommInitRank(&comm, (int)P.world, id, (int)P.rank));
+        struct Handles { cudaIpcMemHandle_t pages, in; };
+        Handles mine; Handles *d_all = nullptr;
+        TW_CUDA(cudaIpcGetMemHandle(&mine.pages, d.pages));
+        TW_CUDA(cudaIpcGetMemHandle(&mine.in, d.in));
+        TW_CUDA(cudaMalloc(&d_all, sizeof(Handles) * P.world));
+        TW_CUDA(cudaMemcpyAsync(d_all + P.rank, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
+        TW_NCCL(g_nccl.AllGather(d_all + P.rank, d_all, sizeof(Handles), kNcclInt8, comm, stream));
+        std::vector<Handles> all(P.world);
+        TW_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * P.world, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        TW_CUDA(cudaFree(d_all));
+        for (uint32_t r = 0; r < P.world; ++r) {
+            if (r == P.rank) continue;
+            void *pp = nullptr, *pi = nullptr;
+            TW_CUDA(cudaIpcOpenMemHandle(&pp, all[r].pages, cudaIpcMemLazyEnablePeerAccess));
+            TW_CUDA(cudaIpcOpenMemHandle(&pi, all[r].in, cudaIpcMemLazyEnablePeerAccess));
+            peer_ptrs.push_back(pp); peer_ptrs.push_back(pi);
+            d.peer_pages[r] = (typename M::Event *)pp; d.peer_in[r] = (LPIn *)pi;
+        }
+        return TW_OK;
+    }
+
+    int barrier_all()
+    {
+        if (P.world <= 1) return TW_OK;
+        // one-double all-reduce doubles as the cross-GPU barrier
+        TW_NCCL(g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream));
+        return TW_OK;
+    }
+
+    int reset() override
+    {
+        k_init<M><<<grid, kBlock, 0, stream>>>(d, P.start_time); count(1);
+        TW_CUDA(cudaGetLastError());
+        TW_CUDA(cudaStreamSynchronize(stream));
+        if (P.world > 1) { int rc = barrier_all(); if (rc) return rc; TW_CUDA(cudaStreamSynchronize(stream)); }
+        return TW_OK;
+    }
+
+    void count(uint64_t n) { launches += n; g_launches += n; }
+
+    int enqueue(const tw_event *evs, size_t n) override
+    {
+        if (n == 0) return TW_OK;
+        if (!evs) { err = "null event buffer"; return TW_ERR_INVALID_ARG; }
+        if (n > stage_cap) {
+            if (d_stage) TW_CUDA(cudaFree(d_stage));
+            d_stage = nullptr; stage_cap = 0;
+            TW_CUDA(cudaMalloc(&d_stage, n * sizeof(tw_event)));
+            stage_cap = n;
+        }
+        TW_CUDA(cudaMemcpyAsync(d_stage, evs, n * sizeof(tw_event), cudaMemcpyHostToDevice, stream));
+        size_t blocks = (n + kBlock - 1) / kBlock; if (blocks > 148 * 16) blocks = 148 * 16;
+        k_route<M><<<(int)blocks, kBlock, 0, stream>>>(d, d_stage, n);
+        k_fold_inject<<<1, 1, 0, stream>>>(d.ctl); count(2);
+        TW_CUDA(cudaGetLastError());
+        if (P.world > 1) { int rc = barrier_all(); if (rc) return rc; }
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        return check_device_error(h_ctl[0]);
+    }
+
+    int check_device_error(const Ctl &c)
+    {
+        if (c.error) {
+            char b[256]; snprintf(b, sizeof b, "%s (LP %u, step %u)", code_name((int)c.error), c.err_lp, c.step);
+            err = b; return (int)c.error;
+        }
+        return TW_OK;
+    }
+
+    int build_graph(uint32_t steps)
+    {
+        if (graph && graph_steps == steps) return TW_OK;
+        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        for (uint32_t i = 0; i < steps; ++i) {
+            k_step<M><<<grid, kBlock, 0, stream>>>(d);
+            if (P.world > 1) {
+                int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);
+                if (e) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); err = "ncclAllReduce failed during capture"; return TW_ERR_CUDA; }
+            }
+        }
+        TW_CUDA(cudaStreamEndCapture(stream, &g));
+        TW_CUDA(cudaGraphInstantiate(&graph, g, 0));
+        TW_CUDA(cudaGraphDestroy(g));
+        graph_steps = steps;
+        return TW_OK;
+    }
+
+    int run(double until, tw_run_stats *st) override
+    {
+        if (!(until <= P.stop_time)) until = P.stop_time;
+        d.stop = until;
+        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }      // d is baked into the kernel node
+        const uint32_t B = P.steps_per_launch ? P.steps_per_launch : 16;
+        int rc = build_graph(B); if (rc) return rc;
+        Ctl c0;
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        c0 = h_ctl[0];
+        const uint64_t launches0 = launches;
+        TW_CUDA(cudaEventRecord(ev0, stream));
+        // pipelined: batch k+1 is enqueued before batch k's control block is inspected
+        int slot = 0; bool pending[2] = {false, false};
+        double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
+        Ctl last = c0;
+        while (!finished) {
+            TW_CUDA(cudaGraphLaunch(graph, stream)); count(B);
+            TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+            TW_CUDA(cudaEventRecord(ev_chk[slot], stream));
+            pending[slot] = true;
+            const int other = slot ^ 1;
+            if (pending[other]) {
+                TW_CUDA(cudaEventSynchronize(ev_chk[other]));
+                pending[other] = false;
+                last = h_ctl[other];
+                if ((result = check_device_error(last)) != TW_OK) break;
+                if (!(last.gvt <= until)) { finished = true; break; }
+                if (last.gvt == last_gvt) { if (++stall > 4096) { err = code_name(TW_ERR_DEADLOCK); result = TW_ERR_DEADLOCK; break; } }
+                else { stall = 0; last_gvt = last.gvt; }
+            }
+            slot = other;
+        }
+        TW_CUDA(cudaEventRecord(ev1, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        for (int s = 0; s < 2; ++s) if (pending[s]) { last = h_ctl[s].c_steps >= last.c_steps ? h_ctl[s] : last; }
+        if (result == TW_OK) result = check_device_error(last);
+        float ms = 0.f; TW_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        // final control block + committed totals
+        TW_CUDA(cudaMemsetAsync(d_tmp, 0, 2 * sizeof(unsigned long long), stream));
+        k_collect<M><<<grid < 1184 ? grid : 1184, kBlock, 0, stream>>>(d, d_tmp); count(1);
+        unsigned long long tot[2];
+        TW_CUDA(cudaMemcpyAsync(tot, d_tmp, sizeof tot, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        const Ctl &c = h_ctl[0];
+        if (result == TW_OK) result = check_device_error(c);
+        if (st) {
+            memset(st, 0, sizeof *st);
+            st->gvt = c.gvt; st->device_ms = ms; st->steps = c.c_steps - c0.c_steps;
+            st->committed = tot[0]; st->trace_hash_sum = tot[1];
+            st->executed = c.c_exec - c0.c_exec; st->rolled_back = c.c_rb_events - c0.c_rb_events;
+            st->rollbacks = c.c_rollbacks - c0.c_rollbacks; st->stragglers = c.c_strag - c0.c_strag;
+            st->anti_sent = c.c_anti - c0.c_anti; st->annihilated = c.c_annih - c0.c_annih; st->retries = c.c_retry - c0.c_retry;
+            st->sent_local = c.c_sent_local - c0.c_sent_local; st->sent_remote = c.c_sent_remote - c0.c_sent_remote;
+            st->kernel_launches = launches - launches0;
+        }
+        return result;
+    }
+
+    int gvt(double *g) override
+    {
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        *g = h_ctl[0].gvt;
+        return TW_OK;
+    }
+
+    int lp_state(uint32_t lp, tw_lp_state *out) override
+    {
+        if (lp < d.lp_base || lp >= d.lp_base + d.n_local) { err = "LP not owned by this partition"; return TW_ERR_INVALID_ARG; }
+        const uint32_t l = lp - d.lp_base;
+        LPHdr h; LPIn in; typename M::State s;
+        TW_CUDA(cudaMemcpyAsync(&h, d.hdr + l, sizeof h, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaMemcpyAsync(&in, d.in + l, sizeof in, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaMemcpyAsync(&s, d.state + l, sizeof s, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        memset(out, 0, sizeof *out);
+        out->lp = lp; out->local_time = h.lvt; out->event_queue_time = h.min_pend;
+        out->event_queue_size = in.total - h.head - h.nproc;
+        out->log_size = h.nproc; out->input_message_count = in.total - h.head; out->output_message_count = h.nproc;
+        out->rollback_count = h_ctl[0].c_rollbacks; out->executed = s.n_exec; out->trace_hash = s.hash;
+        return TW_OK;
+    }
+
+    int read_lp_stats(uint64_t *n_exec, uint64_t *hash, size_t n) override
+    {
+        if (n < d.n_local) { err = "output arrays shorter than the local LP count"; return TW_ERR_INVALID_ARG; }
+        if (d.n_local == 0) return TW_OK;
+        unsigned long long *dn = nullptr, *dh = nullptr;
+        TW_CUDA(cudaMalloc(&dn, sizeof(unsigned long long) * d.n_local));
+        TW_CUDA(cudaMalloc(&dh, sizeof(unsigned long long) * d.n_local));
+        k_gather_stats<M><<<grid, kBlock, 0, stream>>>(d, dn, dh); count(1);
+        TW_CUDA(cudaMemcpyAsync(n_exec, dn, sizeof(uint64_t) * d.n_local, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaMemcpyAsync(hash, dh, sizeof(uint64_t) * d.n_local, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        TW_CUDA(cudaFree(dn)); TW_CUDA(cudaFree(dh));
+        return TW_OK;
+    }
+
+    int read_machrep(tw_machrep_result *out, size_t n) override;
+
+    void partition(uint32_t *base, uint32_t *n) const override { if (base) *base = d.lp_base; if (n) *n = d.n_local; }
+
+    ~Engine() override
+    {
+        if (stream) cudaStreamSynchronize(stream);
+        if (graph) cudaGraphExecDestroy(graph);
+        for (void *p : peer_ptrs) cudaIpcCloseMemHandle(p);
+        if (comm) g_nccl.CommDestroy(comm);
+        cudaFree(d.pages); cudaFree(d.saved); cudaFree(d.state); cudaFree(d.hdr); cudaFree(d.in); cudaFree(d.ctl);
+        cudaFree(d_stage); cudaFree(d_tmp);
+        if (h_ctl) cudaFreeHost(h_ctl);
+        if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+        if (ev_chk[0]) cudaEventDestroy(ev_chk[0]); if (ev_chk[1]) cudaEventDestroy(ev_chk[1]);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+template <> int Engine<PholdModel>::read_machrep(tw_machrep_result *, size_t) { err = "not a MachRep2 engine"; return TW_ERR_NOT_SUPPORTED; }
+template <> int Engine<MachRepModel>::read_machrep(tw_machrep_result *out, size_t n)
+{
+    const uint32_t first_master = ((d.lp_base + 2u) / 3u) * 3u;
+    const uint32_t end = d.lp_base + d.n_local;
+    const uint32_t n_rep = first_master < end ? (end - first_master + 2u) / 3u : 0u;
+    if (n < n_rep) { err = "output array shorter than the local replica count"; return TW_ERR_INVALID_ARG; }
+    if (!n_rep) return TW_OK;
+    tw_machrep_result *dr = nullptr;
+    TW_CUDA(cudaMalloc(&dr, sizeof(tw_machrep_result) * n_rep));
+    k_gather_machrep<<<(n_rep + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, dr, n_rep, P.stop_time); count(1);
+    TW_CUDA(cudaMemcpyAsync(out, dr, sizeof(tw_machrep_result) * n_rep, cudaMemcpyDeviceToHost, stream));
+    TW_CUDA(cudaStreamSynchronize(stream));
+    TW_CUDA(cudaFree(dr));
+    return TW_OK;
+}
+
+}  // namespace twb
+
+// ------------------------------------------------------------------ C ABI
+
+using namespace twb;
+
+struct tw_engine { EngineBase *impl; std::string create_err; };
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+int tw_create(const tw_params *p, tw_engine **out)
+{
+    if (!p || !out) return TW_ERR_INVALID_ARG;
+    *out = nullptr;
+    EngineBase *impl = nullptr; int rc;
+    if (p->model == TW_MODEL_PHOLD) { auto *e = new Engine<PholdModel>(); rc = e->init(*p); impl = e; }
+    else if (p->model == TW_MODEL_MACHREP2) {
+        if (p->n_lps % 3u) { g_create_err = "MachRep2 needs n_lps = 3 * replicas"; return TW_ERR_INVALID_ARG; }
+        auto *e = new Engine<MachRepModel>(); rc = e->init(*p); impl = e;
+    } else { g_create_err = "unknown model"; return TW_ERR_INVALID_ARG; }
+    if (rc != TW_OK) { g_create_err = impl->err; delete impl; return rc; }
+    tw_engine *h = new tw_engine(); h->impl = impl; *out = h;
+    return TW_OK;
+}
+int tw_destroy(tw_engine *e) { if (!e) return TW_ERR_INVALID_ARG; delete e->impl; delete e; return TW_OK; }
+int tw_reset(tw_engine *e) { return e ? e->impl->reset() : TW_ERR_INVALID_ARG; }
+int tw_enqueue_message(tw_engine *e, const tw_event *ev) { return e ? e->impl->enqueue(ev, 1) : TW_ERR_INVALID_ARG; }
+int tw_enqueue_messages(tw_engine *e, const tw_event *evs, size_t n) { return e ? e->impl->enqueue(evs, n) : TW_ERR_INVALID_ARG; }
+int tw_run(tw_engine *e, double until, tw_run_stats *st) { return e ? e->impl->run(until, st) : TW_ERR_INVALID_ARG; }
+int tw_gvt(tw_engine *e, double *g) { return (e && g) ? e->impl->gvt(g) : TW_ERR_INVALID_ARG; }
+int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out) { return (e && out) ? e->impl->lp_state(lp, out) : TW_ERR_INVALID_ARG; }
+int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *hash, size_t n) { return (e && n_exec && hash) ? e->impl->read_lp_stats(n_exec, hash, n) : TW_ERR_INVALID_ARG; }
+int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n) { return (e && out) ? e->impl->read_machrep(out, n) : TW_ERR_INVALID_ARG; }
+int tw_partition(const tw_engine *e, uint32_t *base, uint32_t *n) { if (!e) return TW_ERR_INVALID_ARG; e->impl->partition(base, n); return TW_OK; }
+
+int tw_model_initial_events(const tw_params *p, tw_event *out, size_t cap, size_t *n)
+{
+    if (!p || !out || !n) return TW_ERR_INVALID_ARG;
+    if (p->model == TW_MODEL_PHOLD) *n = PholdModel::initial_events(*p, out, cap);
+    else if (p->model == TW_MODEL_MACHREP2) *n = MachRepModel::initial_events(*p, out, cap);
+    else return TW_ERR_INVALID_ARG;
+    return TW_OK;
+}
+
+int tw_nccl_unique_id(uint8_t out[128])
+{
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_err = err; return TW_ERR_CUDA; }
+    return g_nccl.GetUniqueId(out) == 0 ? TW_OK : TW_ERR_CUDA;
+}
+
+const char *tw_last_error(const tw_engine *e) { return e ? e->impl->err.c_str() : g_create_err.c_str(); }
+const char *tw_strerror(int code) { return code_name(code); }
+const char *tw_version(void) { return "twb200 0.1 sm_100a"; }
+uint64_t tw_kernel_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

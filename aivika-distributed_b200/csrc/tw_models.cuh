@@ -1,0 +1,245 @@
+// tw_models.cuh -- compiled model handlers (device + host).
+//
+// A handler is the device form of `handleSignal messageReceived (\msg -> ... enqueueMessage ...)`
+// (Simulation/Aivika/Distributed/Optimistic/Message.hs:48-86): a pure function
+//   (params, lp, state-before, received event) -> (state-after, sent events)
+// Purity is what lets the engine regenerate anti-messages by replaying the handler on the saved
+// pre-state instead of keeping an OutputMessageQueue (Internal/OutputMessageQueue.hs:81-104).
+//
+// Event.ctr: bits 0..60 = per-sender send counter (part of the saved state, so it is rollback
+// invariant, unlike generateMessageSequenceNo, Internal/OutputMessageQueue.hs:119-122),
+// bit 63 = anti-message toggle (Internal/Message.hs:48), bit 62 = annihilated, bit 61 = processed as no-op.
+#pragma once
+#include "tw_math.cuh"
+#include "../../include/twb200.h"
+
+namespace twb {
+
+constexpr uint64_t kAntiBit = 1ull << 63;
+constexpr uint64_t kDeadBit = 1ull << 62;
+constexpr uint64_t kNoopBit = 1ull << 61;
+constexpr uint64_t kCtrMask = ~(kAntiBit | kDeadBit | kNoopBit);
+
+enum HandlerStatus { H_OK = 0, H_RETRY = 1, H_BAD = 2 };
+
+// ------------------------------------------------------------------ PHOLD
+struct PholdModel {
+    static constexpr int kMaxSends = 1;
+    struct alignas(32) Event {             // 32 B: one DRAM sector
+        double   recv_ts, send_ts;
+        uint64_t ctr;
+        uint32_t src, dst;
+    };
+    struct alignas(32) State {             // 32 B
+        uint64_t rng_ctr, send_ctr, n_exec, hash;
+    };
+    struct Params {
+        uint32_t n_lps, population, remote_pct, n_hot, hot_pct;
+        double   lookahead, mean;
+        uint64_t seed;
+    };
+    static Params make_params(const tw_params &p)
+    {
+        Params m;
+        m.n_lps = p.n_lps; m.population = p.phold.population; m.remote_pct = p.phold.remote_pct;
+        m.n_hot = p.phold.n_hot; m.hot_pct = p.phold.hot_pct;
+        m.lookahead = p.phold.lookahead; m.mean = p.phold.mean; m.seed = p.phold.seed;
+        return m;
+    }
+    TW_HD static State initial_state(const Params &p, uint32_t lp)
+    {
+        State s;
+        s.rng_ctr = p.population; s.send_ctr = p.population; s.n_exec = 0;
+        s.hash = mix_fin(lp_stream_key(p.seed, lp) + 1ull);
+        return s;
+    }
+    TW_HD static Event from_wire(const tw_event &w)
+    {
+        Event e; e.recv_ts = w.recv_ts; e.send_ts = w.send_ts; e.ctr = w.ctr; e.src = w.src; e.dst = w.dst;
+        return e;
+    }
+    // One event execution: draw the delay and the destination, send one message.
+    TW_HD static int handle(const Params &p, uint32_t lp, State &s, const Event &e, Event *out, int &n_out)
+    {
+        const uint64_t key = lp_stream_key(p.seed, lp);
+        const uint64_t d1 = stream_draw(key, s.rng_ctr);
+        const uint64_t d2 = stream_draw(key, s.rng_ctr + 1);
+        const double now = e.recv_ts;
+        const double delay = fadd(p.lookahead, expo_variate(uniform01(d1), p.mean));
+        uint32_t dst = lp;
+        const uint64_t N = p.n_lps;
+        if (N > 1 && (((d2 >> 32) * 100ull) >> 32) < p.remote_pct) {
+            const uint64_t d3 = stream_draw(key, s.rng_ctr + 2);
+            const uint64_t d4 = stream_draw(key, s.rng_ctr + 3);
+            if (p.n_hot > 0 && (((d4 >> 32) * 100ull) >> 32) < p.hot_pct) {
+                const uint64_t k = mulhi64(d3, p.n_hot);
+                dst = (uint32_t)((k * N) / p.n_hot);
+            } else {
+                const uint64_t k = mulhi64(d3, N - 1);
+                dst = (uint32_t)(k + (k >= lp ? 1u : 0u));
+            }
+        }
+        Event &o = out[0];
+        o.recv_ts = fadd(now, delay); o.send_ts = now; o.ctr = s.send_ctr; o.src = lp; o.dst = dst;
+        n_out = 1;
+        s.hash = trace_fold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
+        s.rng_ctr += 4; s.send_ctr += 1; s.n_exec += 1;
+        return H_OK;
+    }
+    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap)
+    {
+        Params p = make_params(tp);
+        size_t n = 0;
+        for (uint32_t i = 0; i < p.n_lps; ++i) {
+            const uint64_t key = lp_stream_key(p.seed, i);
+            for (uint32_t j = 0; j < p.population; ++j) {
+                if (n >= cap) return n;
+                tw_event &e = out[n++];
+                e.recv_ts = expo_variate(uniform01(stream_draw(key, j)), p.mean);
+                e.send_ts = 0.0; e.ctr = j; e.src = i; e.dst = i; e.type = 0; e.pad = 0; e.value = 0.0;
+            }
+        }
+        return n;
+    }
+};
+
+// ------------------------------------------------------------------ MachRep2
+// LP 3r = masterModel, LP 3r+1 / 3r+2 = slaveModel 1 / 2 of replica r
+// (tests/MachRep2DistributedReproducible.hs:125-229).
+struct MachRepModel {
+    static constexpr int kMaxSends = 3;
+    struct alignas(16) Event {             // 48 B
+        double   recv_ts, send_ts;
+        uint64_t ctr;
+        uint32_t src, dst;
+        uint32_t type, pad;
+        double   value;
+    };
+    struct alignas(16) State {             // 64 B; master and slave views share the record
+        double   total_up_time;            // master :167
+        int64_t  n_rep, n_immed;           // master :168-169
+        int32_t  count;                    // master: resourceCount of the FCFS repairPerson (:171-172)
+        uint8_t  wait[3];                  // master: FCFS wait list (Optimistic/QueueStrategy.hs:24-45)
+        uint8_t  wait_len;
+        StdGen   gen;                      // slave: Ref DIO StdGen (:77-78), rolled back with the state
+        uint64_t send_ctr, n_exec, hash;
+    };
+    struct Params {
+        uint32_t n_lps;
+        double mean_up, mean_rep, delta;
+        int64_t seed1, seed2, stride;
+    };
+    static Params make_params(const tw_params &p)
+    {
+        Params m; m.n_lps = p.n_lps; m.mean_up = p.machrep.mean_up_time; m.mean_rep = p.machrep.mean_repair_time;
+        m.delta = p.machrep.delta; m.seed1 = p.machrep.seed1; m.seed2 = p.machrep.seed2; m.stride = p.machrep.seed_stride;
+        return m;
+    }
+    TW_HD static State initial_state(const Params &p, uint32_t lp)
+    {
+        State s;
+        s.total_up_time = 0.0; s.n_rep = 0; s.n_immed = 0; s.count = 1; s.wait_len = 0;
+        s.wait[0] = s.wait[1] = s.wait[2] = 0;
+        const uint32_t role = lp % 3u, r = lp / 3u;
+        s.gen.s1 = 0; s.gen.s2 = 0;
+        if (role == 1) s.gen = mk_std_gen(p.seed1 + (int64_t)r * p.stride);
+        if (role == 2) s.gen = mk_std_gen(p.seed2 + (int64_t)r * p.stride);
+        s.send_ctr = role ? 1ull : 0ull;   // slaves: ctr 0 is the START self-event
+        s.n_exec = 0;
+        s.hash = mix_fin(lp_stream_key(0, lp) + 1ull);
+        return s;
+    }
+    TW_HD static Event from_wire(const tw_event &w)
+    {
+        Event e; e.recv_ts = w.recv_ts; e.send_ts = w.send_ts; e.ctr = w.ctr; e.src = w.src; e.dst = w.dst;
+        e.type = w.type; e.pad = 0; e.value = w.value;
+        return e;
+    }
+    TW_HD static void send(State &s, uint32_t from, uint32_t to, double now, double at, uint32_t type, double value,
+                           Event *out, int &n_out)
+    {
+        Event &o = out[n_out++];
+        o.recv_ts = at; o.send_ts = now; o.ctr = s.send_ctr++; o.src = from; o.dst = to; o.type = type; o.pad = 0; o.value = value;
+    }
+    TW_HD static int handle(const Params &p, uint32_t lp, State &s, const Event &e, Event *out, int &n_out)
+    {
+        const uint32_t role = lp % 3u, master = lp - role;
+        const double t = e.recv_ts, td = fadd(t, p.delta);
+        n_out = 0;
+        if (role != 0) {
+            switch (e.type) {
+            case TW_MR_START:
+            case TW_MR_RELEASE_REPAIR_PERSON_RESP: {          // machine, :130-135 / :150-154
+                const double up = expo_variate(std_random_double(s.gen), p.mean_up);
+                const double at = fadd(td, up);
+                send(s, lp, master, t, at, TW_MR_TOTAL_UP_TIME_CHANGE, up, out, n_out);
+                send(s, lp, master, t, at, TW_MR_NREP_CHANGE, 1.0, out, n_out);
+                send(s, lp, master, t, at, TW_MR_REPAIR_PERSON_COUNT, 0.0, out, n_out);
+                break; }
+            case TW_MR_REPAIR_PERSON_COUNT_RESP:              // :137-142
+                if ((int64_t)e.value == 1) send(s, lp, master, t, td, TW_MR_NIMMED_REP_CHANGE, 1.0, out, n_out);
+                send(s, lp, master, t, td, TW_MR_REQUEST_REPAIR_PERSON, 0.0, out, n_out);
+                break;
+            case TW_MR_REQUEST_REPAIR_PERSON_RESP: {          // :144-148
+                const double rt = expo_variate(std_random_double(s.gen), p.mean_rep);
+                send(s, lp, master, t, fadd(td, rt), TW_MR_RELEASE_REPAIR_PERSON, 0.0, out, n_out);
+                break; }
+            default: break;                                    // responses nobody subscribed to
+            }
+        } else {
+            const uint32_t from = e.src;
+            switch (e.type) {
+            case TW_MR_TOTAL_UP_TIME_CHANGE:                  // :176-180
+                s.total_up_time = fadd(s.total_up_time, e.value);
+                send(s, lp, from, t, td, TW_MR_TOTAL_UP_TIME_CHANGE_RESP, 0.0, out, n_out); break;
+            case TW_MR_NREP_CHANGE:                           // :182-186
+                s.n_rep += (int64_t)e.value;
+                send(s, lp, from, t, td, TW_MR_NREP_CHANGE_RESP, 0.0, out, n_out); break;
+            case TW_MR_NIMMED_REP_CHANGE:                     // :188-192
+                s.n_immed += (int64_t)e.value;
+                send(s, lp, from, t, td, TW_MR_NIMMED_REP_CHANGE_RESP, 0.0, out, n_out); break;
+            case TW_MR_REPAIR_PERSON_COUNT:                   // :194-198
+                send(s, lp, from, t, td, TW_MR_REPAIR_PERSON_COUNT_RESP, (double)s.count, out, n_out); break;
+            case TW_MR_REQUEST_REPAIR_PERSON:                 // :200-206 requestResource
+                if (s.count == 0) {
+                    if (s.wait_len >= 3) return H_RETRY;       // only reachable from a stale optimistic state
+                    s.wait[s.wait_len++] = (uint8_t)(from - master);
+                } else {
+                    s.count -= 1;
+                    send(s, lp, from, t, td, TW_MR_REQUEST_REPAIR_PERSON_RESP, 0.0, out, n_out);
+                }
+                break;
+            case TW_MR_RELEASE_REPAIR_PERSON: {               // :208-212 releaseResourceWithinEvent
+                const int32_t c1 = s.count + 1;
+                if (c1 > 1) return H_RETRY;                    // SimulationRetry (Internal/Event.hs:247-249, 768-813)
+                uint32_t waiter = 0; bool resumed = false;
+                if (s.wait_len == 0) s.count = c1;
+                else {
+                    waiter = master + s.wait[0]; resumed = true;
+                    s.wait[0] = s.wait[1]; s.wait[1] = s.wait[2]; s.wait[2] = 0; s.wait_len--;
+                }
+                send(s, lp, from, t, td, TW_MR_RELEASE_REPAIR_PERSON_RESP, 0.0, out, n_out);
+                if (resumed) send(s, lp, waiter, t, td, TW_MR_REQUEST_REPAIR_PERSON_RESP, 0.0, out, n_out);
+                break; }
+            default: break;
+            }
+        }
+        s.hash = trace_fold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
+        if (e.type != TW_MR_START) s.n_exec += 1;
+        return H_OK;
+    }
+    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap)
+    {
+        size_t n = 0;
+        for (uint32_t lp = 0; lp < tp.n_lps; ++lp) {
+            if (lp % 3u == 0) continue;                        // runEventInStartTime machine, :154
+            if (n >= cap) return n;
+            tw_event &e = out[n++];
+            e.recv_ts = tp.start_time; e.send_ts = tp.start_time; e.ctr = 0; e.src = lp; e.dst = lp;
+            e.type = TW_MR_START; e.pad = 0; e.value = 0.0;
+        }
+        return n;
+    }
+};
+
+}  // namespace twb

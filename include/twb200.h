@@ -1,0 +1,206 @@
+/*
+ * twb200.h -- C ABI of the B200-native Time Warp engine (libtwb200.so).
+ *
+ * This is the drop-in boundary for the logical-process hot path of
+ * dsorokin/aivika-distributed.  The reference has no FFI (it is 100 % Haskell), so each
+ * entry point below names the reference interface it stands in for; the Haskell
+ * `foreign import ccall` stubs a maintainer would add are in INTEGRATION.md and
+ * aivika-distributed_b200/hs/.  All paths are relative to /root/reference/.
+ *
+ * Conventions: every function returns an int status (TW_OK == 0); the engine handle is
+ * single-owner and not thread-safe (one LP is mutated by exactly one process in the
+ * reference too: Simulation/Aivika/Distributed/Optimistic/Internal/DIO.hs:427-476 and the
+ * queueBusy guard, Internal/Event.hs:199-208); pointer arguments are HOST pointers borrowed
+ * for the duration of the call; outputs are caller-allocated.  There is no CPU fallback:
+ * tw_create fails with TW_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef TWB200_H
+#define TWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tw_engine tw_engine;
+
+/* ---- status codes: the reference's `error` strings become distinct codes ---- */
+enum {
+    TW_OK = 0,
+    TW_ERR_INVALID_ARG        = 1,
+    TW_ERR_CUDA               = 2,   /* CUDA/NCCL failure or no usable device */
+    TW_ERR_SEND_AFTER_RECV    = 3,   /* "The Send time cannot be greater than the Receive message time" Internal/OutputMessageQueue.hs:67-68 */
+    TW_ERR_OUTDATED_MESSAGE   = 4,   /* "Received the outdated message" Internal/Event.hs:370-374 */
+    TW_ERR_QUEUE_OVERFLOW     = 5,   /* fixed-capacity analogue of isEventOverflow, Internal/Event.hs:289-306 */
+    TW_ERR_ANTI_UNMATCHED     = 6,   /* "Cannot annihilate another message" Internal/InputMessageQueue.hs:273-274 */
+    TW_ERR_DEADLOCK           = 7,   /* "Detected a deadlock when retrying the computations" Internal/Event.hs:809-812 */
+    TW_ERR_TIME_ORDER         = 8,   /* "The time value is too small" Internal/Event.hs:223-227 */
+    TW_ERR_BAD_DESTINATION    = 9,   /* receiver id outside [0, n_lps) */
+    TW_ERR_MODEL              = 10,  /* model handler reached an impossible state at GVT */
+    TW_ERR_OUTBOX_OVERFLOW    = 11,  /* cross-GPU staging buffer full */
+    TW_ERR_NOT_SUPPORTED      = 12
+};
+
+enum { TW_MODEL_PHOLD = 1, TW_MODEL_MACHREP2 = 2 };
+
+/* MachRep2 message kinds == the message data types of tests/MachRep2DistributedReproducible.hs:88-104 */
+enum {
+    TW_MR_START = 0,
+    TW_MR_TOTAL_UP_TIME_CHANGE = 1, TW_MR_NREP_CHANGE = 2, TW_MR_NIMMED_REP_CHANGE = 3,
+    TW_MR_REPAIR_PERSON_COUNT = 4, TW_MR_REQUEST_REPAIR_PERSON = 5, TW_MR_RELEASE_REPAIR_PERSON = 6,
+    TW_MR_TOTAL_UP_TIME_CHANGE_RESP = 7, TW_MR_NREP_CHANGE_RESP = 8, TW_MR_NIMMED_REP_CHANGE_RESP = 9,
+    TW_MR_REPAIR_PERSON_COUNT_RESP = 10, TW_MR_REQUEST_REPAIR_PERSON_RESP = 11, TW_MR_RELEASE_REPAIR_PERSON_RESP = 12
+};
+
+/*
+ * One timestamped message at the boundary (48 bytes).  Replaces `Message`
+ * (Internal/Message.hs:37-54): sequenceNo -> ctr, sendTime, receiveTime, senderId -> src,
+ * receiverId -> dst, antiToggle -> bit 63 of ctr, messageData -> (type, value).
+ */
+typedef struct tw_event {
+    double   recv_ts;
+    double   send_ts;
+    uint64_t ctr;
+    uint32_t src;
+    uint32_t dst;
+    uint32_t type;
+    uint32_t pad;
+    double   value;
+} tw_event;
+
+typedef struct tw_phold_params {
+    uint32_t population;   /* initial events per LP */
+    uint32_t remote_pct;   /* 0..100 */
+    uint32_t n_hot;        /* hot-set size for skewed fan-out, 0 = uniform */
+    uint32_t hot_pct;      /* share of remote messages sent to the hot set */
+    double   lookahead;
+    double   mean;
+    uint64_t seed;
+} tw_phold_params;
+
+/* constants of tests/MachRep2DistributedReproducible.hs:61-74 */
+typedef struct tw_machrep_params {
+    double  mean_up_time;      /* 1.0 */
+    double  mean_repair_time;  /* 0.5 */
+    double  delta;             /* 1e-6 */
+    int64_t seed1, seed2;      /* 456, 789 */
+    int64_t seed_stride;       /* replica r uses seed + r*stride */
+} tw_machrep_params;
+
+/*
+ * Engine parameters.  Hot-path fields of DIOParams (Internal/DIO.hs:75-84, defaults :200-204)
+ * plus the Specs start/stop times and the partition description.
+ */
+typedef struct tw_params {
+    uint32_t model;               /* TW_MODEL_* */
+    uint32_t n_lps;               /* global LP count (MachRep2: 3 * replicas) */
+    uint32_t rank, world;         /* this partition / number of partitions (GPUs); LP i lives on i / ceil(n_lps/world) */
+    int32_t  device;              /* CUDA device ordinal, -1 = current */
+    uint32_t queue_capacity;      /* per-LP slots (power of two); ~ dioUndoableLogSizeThreshold / dioOutputMessageQueueSizeThreshold */
+    uint32_t max_events_per_step; /* optimistic batch per LP per super-step, 1..4 */
+    uint32_t steps_per_launch;    /* super-steps per graph launch between host GVT checks */
+    double   start_time;          /* spcStartTime */
+    double   stop_time;           /* spcStopTime (inclusive, Internal/Event.hs:228-229) */
+    double   time_horizon;        /* dioTimeHorizon; < 0 or NaN == Nothing (unbounded optimism) */
+    uint32_t proc_limit;          /* processed-but-uncommitted entries per LP before optimism stalls (0 = capacity/4) */
+    uint32_t fossil_threshold;    /* lazy fossil collection trigger (0 = capacity/8) */
+    uint32_t outbox_capacity;     /* reserved (cross-GPU staging) */
+    uint32_t flags;               /* reserved */
+    tw_phold_params   phold;
+    tw_machrep_params machrep;
+    uint8_t  nccl_id[128];        /* ncclUniqueId shared by all ranks when world > 1 (tw_nccl_unique_id) */
+} tw_params;
+
+/* Result of tw_run: counters the reference never kept next to its lpStateRollbackCount. */
+typedef struct tw_run_stats {
+    double   gvt;                 /* global virtual time at return */
+    double   device_ms;           /* CUDA-event time of the run on this device */
+    uint64_t steps;               /* super-steps executed */
+    uint64_t committed;           /* committed handler executions on this partition */
+    uint64_t executed;            /* executed incl. rolled back */
+    uint64_t rolled_back;         /* executions undone */
+    uint64_t rollbacks;           /* rollback episodes (lpStateRollbackCount summed) */
+    uint64_t stragglers;
+    uint64_t anti_sent;
+    uint64_t annihilated;
+    uint64_t retries;             /* SimulationRetry stalls */
+    uint64_t sent_local, sent_remote;
+    uint64_t kernel_launches;     /* launches of this library's kernels during the run */
+    uint64_t trace_hash_sum;      /* sum over local LPs of the per-LP committed-trace hash */
+} tw_run_stats;
+
+/* Mirrors LogicalProcessState (Simulation/Aivika/Distributed/Optimistic/State.hs:27-54). */
+typedef struct tw_lp_state {
+    uint32_t lp;
+    double   local_time;               /* lpStateLocalTime  */
+    double   event_queue_time;         /* lpStateEventQueueTime (min pending) */
+    uint32_t event_queue_size;         /* lpStateEventQueueSize (pending) */
+    uint32_t log_size;                 /* lpStateLogSize (processed, uncommitted) */
+    uint32_t input_message_count;      /* lpStateInputMessageCount */
+    uint32_t output_message_count;     /* lpStateOutputMessageCount (regenerated by replay: processed entries) */
+    uint64_t rollback_count;           /* lpStateRollbackCount (engine-wide; per-LP not kept) */
+    uint64_t executed;                 /* committed handler executions of this LP */
+    uint64_t trace_hash;
+} tw_lp_state;
+
+/* Per-replica MachRep2 result: the pair returned by masterModel (:214-229). */
+typedef struct tw_machrep_result {
+    double  total_up_time;
+    int64_t n_rep;
+    int64_t n_immed_rep;
+    double  up_time_prop;
+    double  immed_prop;
+} tw_machrep_result;
+
+/* runDIO / newEventQueue (Internal/DIO.hs:327-328, Internal/Event.hs:92-116): allocate all LP state on the device. */
+int tw_create(const tw_params *params, tw_engine **out);
+/* terminateDIO / unregisterDIO (Internal/DIO.hs:246-305). */
+int tw_destroy(tw_engine *e);
+/* Back to start_time with empty queues (a new runSimulation on the same LPs). */
+int tw_reset(tw_engine *e);
+
+/* enqueueMessage pid t a issued from runEventInStartTime (Optimistic/Message.hs:48-69): host-side injection. */
+int tw_enqueue_message(tw_engine *e, const tw_event *ev);
+/* QueueMessageBulk (Internal/Message.hs:113-116, Internal/Event.hs:382-405): n messages from a host buffer.
+ * Messages whose dst is owned by another partition are ignored (each rank passes the same buffer or its own slice). */
+int tw_enqueue_messages(tw_engine *e, const tw_event *evs, size_t n);
+
+/* runEventInStopTime (Internal/Event.hs:124-129, 743-752): advance until GVT passes until_time
+ * (the reference returns when its GVT copy equals the stop time, :717-730). */
+int tw_run(tw_engine *e, double until_time, tw_run_stats *stats);
+
+/* GlobalTimeMessage (Internal/TimeServer.hs:384-403): current GVT. */
+int tw_gvt(tw_engine *e, double *gvt);
+
+/* ProvideLogicalProcessStateMessage / sendState (Internal/Event.hs:468-475, 910-942). lp is a global id owned by this rank. */
+int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out);
+
+/* Per-LP committed-event counts and trace hashes for the LPs of this partition (n = local LP count). */
+int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *trace_hash, size_t n);
+/* MachRep2: results of the replicas whose master lives on this partition. */
+int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n_replicas);
+
+/* Partition geometry: first global LP id and LP count owned by this rank. */
+int tw_partition(const tw_engine *e, uint32_t *lp_base, uint32_t *n_local);
+
+/* Synthetic model inputs (host-side, bit-identical to what the device handler would draw):
+ * PHOLD initial population (n_lps*population events) / MachRep2 START events (2 per replica).
+ * Writes at most cap events, returns the count in *n. */
+int tw_model_initial_events(const tw_params *params, tw_event *out, size_t cap, size_t *n);
+
+/* ncclGetUniqueId for multi-GPU runs; rank 0 calls it and distributes the 128 bytes. */
+int tw_nccl_unique_id(uint8_t out[128]);
+
+const char *tw_last_error(const tw_engine *e);
+const char *tw_strerror(int code);
+/* Library identification: "twb200 <version> sm_100a". */
+const char *tw_version(void);
+/* Number of kernels this library has launched in this process (all engines). */
+uint64_t tw_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

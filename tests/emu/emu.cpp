@@ -1,0 +1,120 @@
+// emu.cpp -- TEST INFRASTRUCTURE ONLY (never linked into libtwb200.so, never used by bench.py).
+//
+// Compiles the engine's device functions (tw_core.cuh: lp_step / emit_event / route_event and the model
+// handlers) with g++ and drives them sequentially on the CPU: one "kernel launch" = a loop over all LPs of
+// all emulated partitions in a shuffled order.  Purpose: debug the rollback / annihilation / GVT logic of
+// the exact source the GPU runs, in a container that has no GPU, and exercise the multi-partition (world > 1)
+// addressing without NVLink.  It is a development aid and a `-m "not gpu"` test of the host-side logic; parity
+// claims are made only by the `-m gpu` tests that call the CUDA build through the C ABI.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../aivika-distributed_b200/csrc/tw_core.cuh"
+
+using namespace twb;
+
+template <class M>
+struct Part {
+    Dev<M> d;
+    std::vector<typename M::Event> pages;
+    std::vector<typename M::State> saved, state;
+    std::vector<LPHdr> hdr;
+    std::vector<LPIn> in;
+};
+
+static uint64_t rng_next(uint64_t &s) { s += kGolden; return mix_fin(s); }
+
+template <class M>
+static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,
+                     tw_machrep_result *mr, tw_run_stats *st)
+{
+    const uint32_t W = p->world ? p->world : 1;
+    if (W > (uint32_t)kMaxWorld) return TW_ERR_INVALID_ARG;
+    const uint32_t cap = p->queue_capacity ? p->queue_capacity : 128;
+    std::vector<Part<M>> parts(W);
+    uint32_t n_per = (p->n_lps + W - 1) / W;
+    if (std::is_same<M, MachRepModel>::value && W > 1) n_per = ((n_per + 2) / 3) * 3;
+    for (uint32_t r = 0; r < W; ++r) {
+        Part<M> &P = parts[r]; Dev<M> &d = P.d;
+        memset(&d, 0, sizeof d);
+        d.n_global = p->n_lps; d.world = W; d.rank = r; d.n_per = n_per; d.lp_base = n_per * r;
+        d.n_local = d.lp_base >= p->n_lps ? 0 : std::min(n_per, p->n_lps - d.lp_base);
+        d.cap = cap; d.mask = cap - 1;
+        d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : kMaxBatch;
+        d.proc_limit = p->proc_limit ? p->proc_limit : cap / 4;
+        d.fossil_thresh = p->fossil_threshold ? p->fossil_threshold : cap / 8;
+        d.stop = p->stop_time; d.horizon = (p->time_horizon >= 0.0) ? p->time_horizon : -1.0;
+        d.mp = M::make_params(*p);
+        const size_t nl = std::max<size_t>(d.n_local, 1);
+        P.pages.resize(nl * cap); P.saved.resize(nl * cap); P.state.resize(nl); P.hdr.resize(nl); P.in.resize(nl);
+        d.pages = P.pages.data(); d.saved = P.saved.data(); d.state = P.state.data(); d.hdr = P.hdr.data(); d.in = P.in.data();
+        for (uint32_t l = 0; l < d.n_local; ++l) {
+            LPHdr h; h.head = h.nproc = h.consumed = h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
+            P.hdr[l] = h; LPIn in; in.total = in.cnt[0] = in.cnt[1] = in.pad = 0; P.in[l] = in;
+            P.state[l] = M::initial_state(d.mp, d.lp_base + l);
+        }
+    }
+    for (uint32_t r = 0; r < W; ++r)
+        for (uint32_t q = 0; q < W; ++q) { parts[r].d.peer_pages[q] = parts[q].d.pages; parts[r].d.peer_in[q] = parts[q].d.in; }
+
+    // initial events through the same routing function the k_route kernel uses
+    std::vector<tw_event> init((size_t)p->n_lps * (p->model == TW_MODEL_PHOLD ? p->phold.population : 1) + 8);
+    size_t n_init = 0;
+    if (p->model == TW_MODEL_PHOLD) n_init = PholdModel::initial_events(*p, init.data(), init.size());
+    else n_init = MachRepModel::initial_events(*p, init.data(), init.size());
+    uint32_t step = 0; double gvt = p->start_time;
+    Acc acc; acc.init();
+    for (uint32_t r = 0; r < W; ++r)
+        for (size_t i = 0; i < n_init; ++i) route_event<M>(parts[r].d, acc, (step & 1u) ^ 1u, init[i]);
+    if (acc.err) return (int)acc.err;
+    gvt = std::min(gvt, acc.emit_min);
+
+    std::vector<std::pair<uint32_t, uint32_t>> order;
+    for (uint32_t r = 0; r < W; ++r) for (uint32_t l = 0; l < parts[r].d.n_local; ++l) order.push_back({r, l});
+    uint64_t rs = shuffle_seed;
+    tw_run_stats S; memset(&S, 0, sizeof S);
+    uint64_t stall = 0;
+    while (gvt <= p->stop_time) {
+        double wend = p->stop_time;
+        if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
+        if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
+        acc.init();
+        for (auto &o : order) lp_step<M>(parts[o.first].d, acc, o.second, gvt, wend, step & 1u);
+        if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
+        const double g = std::min(acc.pend_min, acc.emit_min);
+        if (g < gvt) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", gvt, g, step); return 100; }
+        if (g == gvt) { if (++stall > 100000) return TW_ERR_DEADLOCK; } else stall = 0;
+        gvt = g; step++;
+        S.steps++; S.executed += acc.exec; S.rolled_back += acc.rb_events; S.rollbacks += acc.rollbacks; S.stragglers += acc.strag;
+        S.anti_sent += acc.anti; S.annihilated += acc.annih; S.retries += acc.retry; S.sent_local += acc.sent_local; S.sent_remote += acc.sent_remote;
+    }
+    S.gvt = gvt;
+    for (uint32_t r = 0; r < W; ++r)
+        for (uint32_t l = 0; l < parts[r].d.n_local; ++l) {
+            const uint32_t lp = parts[r].d.lp_base + l;
+            if (n_exec) n_exec[lp] = parts[r].state[l].n_exec;
+            if (hash) hash[lp] = parts[r].state[l].hash;
+            S.committed += parts[r].state[l].n_exec; S.trace_hash_sum += parts[r].state[l].hash;
+        }
+    if (st) *st = S;
+    if (mr) {
+        if constexpr (std::is_same<M, MachRepModel>::value) {
+            for (uint32_t lp = 0; lp < p->n_lps; lp += 3) {
+                const uint32_t r = lp / n_per; const MachRepModel::State &s = parts[r].state[lp - parts[r].d.lp_base];
+                tw_machrep_result &o = mr[lp / 3];
+                o.total_up_time = s.total_up_time; o.n_rep = s.n_rep; o.n_immed_rep = s.n_immed;
+                o.up_time_prop = s.total_up_time / (2.0 * p->stop_time); o.immed_prop = (double)s.n_immed / (double)s.n_rep;
+            }
+        }
+    }
+    return TW_OK;
+}
+
+extern "C" int emu_run(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,
+                       tw_machrep_result *mr, tw_run_stats *st)
+{
+    if (p->model == TW_MODEL_PHOLD) return emu_run_t<PholdModel>(p, shuffle_seed, n_exec, hash, mr, st);
+    if (p->model == TW_MODEL_MACHREP2) return emu_run_t<MachRepModel>(p, shuffle_seed, n_exec, hash, mr, st);
+    return TW_ERR_INVALID_ARG;
+}
