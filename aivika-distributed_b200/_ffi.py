@@ -25,7 +25,7 @@ ERROR_NAMES = {
 # every symbol include/twb200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
-    "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_model_initial_events",
+    "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_model_initial_events", "tw_model_initial_events_range",
     "tw_nccl_unique_id", "tw_last_error", "tw_strerror", "tw_version", "tw_kernel_launch_count",
 ]
 
@@ -104,6 +104,9 @@ def load(path=None):
     lib.tw_partition.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; lib.tw_partition.restype = C.c_int
     lib.tw_model_initial_events.argtypes = [C.POINTER(tw_params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.tw_model_initial_events.restype = C.c_int
+    lib.tw_model_initial_events_range.argtypes = [C.POINTER(tw_params), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+                                                  C.POINTER(C.c_size_t)]
+    lib.tw_model_initial_events_range.restype = C.c_int
     lib.tw_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8 * 128)]; lib.tw_nccl_unique_id.restype = C.c_int
     lib.tw_last_error.argtypes = [H]; lib.tw_last_error.restype = C.c_char_p
     lib.tw_strerror.argtypes = [C.c_int]; lib.tw_strerror.restype = C.c_char_p

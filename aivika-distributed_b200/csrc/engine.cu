@@ -623,6 +623,15 @@ int tw_model_initial_events(const tw_params *p, tw_event *out, size_t cap, size_
     return TW_OK;
 }
 
+int tw_model_initial_events_range(const tw_params *p, uint32_t lp0, uint32_t lp1, tw_event *out, size_t cap, size_t *n)
+{
+    if (!p || !out || !n) return TW_ERR_INVALID_ARG;
+    if (p->model == TW_MODEL_PHOLD) *n = PholdModel::initial_events(*p, out, cap, lp0, lp1);
+    else if (p->model == TW_MODEL_MACHREP2) *n = MachRepModel::initial_events(*p, out, cap, lp0, lp1);
+    else return TW_ERR_INVALID_ARG;
+    return TW_OK;
+}
+
 int tw_nccl_unique_id(uint8_t out[128])
 {
     std::string err;

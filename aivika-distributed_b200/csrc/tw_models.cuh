@@ -86,11 +86,11 @@ struct PholdModel {
         s.rng_ctr += 4; s.send_ctr += 1; s.n_exec += 1;
         return H_OK;
     }
-    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap)
+    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
         Params p = make_params(tp);
         size_t n = 0;
-        for (uint32_t i = 0; i < p.n_lps; ++i) {
+        for (uint32_t i = lp0; i < p.n_lps && i < lp1; ++i) {
             const uint64_t key = lp_stream_key(p.seed, i);
             for (uint32_t j = 0; j < p.population; ++j) {
                 if (n >= cap) return n;
@@ -228,10 +228,10 @@ struct MachRepModel {
         if (e.type != TW_MR_START) s.n_exec += 1;
         return H_OK;
     }
-    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap)
+    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
         size_t n = 0;
-        for (uint32_t lp = 0; lp < tp.n_lps; ++lp) {
+        for (uint32_t lp = lp0; lp < tp.n_lps && lp < lp1; ++lp) {
             if (lp % 3u == 0) continue;                        // runEventInStartTime machine, :154
             if (n >= cap) return n;
             tw_event &e = out[n++];

@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's DIO surface for the batched Time Warp path.
+
+Names, argument meaning and error behaviour follow the reference (paths relative to /root/reference):
+  DIOParams / defaultDIOParams   Simulation/Aivika/Distributed/Optimistic/Internal/DIO.hs:70-110, 196-217
+  Specs                          aivika-transformers (spcStartTime / spcStopTime), used at tests/MachRep2DistributedReproducible.hs:64-68
+  runDIO                         Internal/DIO.hs:327-328
+  enqueueMessage / sendMessage   Optimistic/Message.hs:41-69
+  timeServer / TimeServerParams  Internal/TimeServer.hs:47-72, 485
+  LogicalProcessState            Optimistic/State.hs:27-54
+The reference runs one Haskell closure per event; the device runs a *compiled* handler for a whole batch of
+homogeneous LPs, so a run is described by a model descriptor (PHOLD / MachRep2) instead of a closure.
+Everything executes on the GPU through libtwb200.so (include/twb200.h); there is no CPU path here.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi as ffi
+
+
+class SimulationAbort(RuntimeError):
+    """Raised when the engine reports a non-zero status (the reference raises `error`/SimulationAbort)."""
+
+    def __init__(self, code, message):
+        super().__init__(f"{ffi.ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+# ---------------------------------------------------------------- parameters (reference field names)
+@dataclass
+class DIOParams:
+    dioLoggingPriority: str = "WARNING"
+    dioName: str = "LP"
+    dioTimeHorizon: Optional[float] = None                  # Nothing = unbounded optimism
+    dioUndoableLogSizeThreshold: int = 10_000_000           # mapped onto the per-LP ring capacity
+    dioOutputMessageQueueSizeThreshold: int = 10_000
+    dioTransientMessageQueueSizeThreshold: int = 5_000
+    dioSyncTimeout: int = 60_000_000
+    dioAllowPrematureIO: bool = False
+    dioAllowSkippingOutdatedMessage: bool = False           # outdated messages are always an error here
+    # engine-specific knobs (no reference counterpart)
+    queueCapacity: int = 128
+    maxEventsPerStep: int = 4
+    stepsPerLaunch: int = 16
+    procLimit: int = 0
+    fossilThreshold: int = 0
+
+
+defaultDIOParams = DIOParams()
+
+
+@dataclass
+class Specs:
+    spcStartTime: float = 0.0
+    spcStopTime: float = 1000.0
+    spcDT: float = 1.0
+
+
+@dataclass
+class TimeServerParams:
+    tsLoggingPriority: str = "WARNING"
+    tsName: str = "Time Server"
+    tsTimeSyncDelay: int = 100_000      # the device engine reduces GVT every super-step instead
+
+
+defaultTimeServerParams = TimeServerParams()
+
+
+@dataclass
+class TimeServer:
+    """The Time Server role (Internal/TimeServer.hs:485): quorum of LPs + the global virtual time."""
+    quorum: int
+    params: TimeServerParams = field(default_factory=TimeServerParams)
+    _dio: Optional["DIO"] = None
+
+    def globalTime(self):
+        if self._dio is None:
+            return None
+        return self._dio.globalTime()
+
+
+def timeServer(n, params=defaultTimeServerParams):
+    return TimeServer(n, params)
+
+
+# ---------------------------------------------------------------- model descriptors (compiled handlers)
+@dataclass
+class PHOLD:
+    n_lps: int
+    population: int = 16
+    remote_pct: int = 10
+    lookahead: float = 0.1
+    mean: float = 1.0
+    seed: int = 1
+    n_hot: int = 0
+    hot_pct: int = 0
+
+    def fill(self, p):
+        p.model = ffi.TW_MODEL_PHOLD; p.n_lps = self.n_lps
+        p.phold.population = self.population; p.phold.remote_pct = self.remote_pct
+        p.phold.n_hot = self.n_hot; p.phold.hot_pct = self.hot_pct
+        p.phold.lookahead = self.lookahead; p.phold.mean = self.mean; p.phold.seed = self.seed
+
+
+@dataclass
+class MachRep2:
+    """tests/MachRep2DistributedReproducible.hs replicated `n_replicas` times (LP 3r master, 3r+1/3r+2 slaves)."""
+    n_replicas: int = 1
+    meanUpTime: float = 1.0
+    meanRepairTime: float = 0.5
+    delta: float = 1e-6
+    seeds: tuple = (456, 789)
+    seed_stride: int = 1000
+
+    def fill(self, p):
+        p.model = ffi.TW_MODEL_MACHREP2; p.n_lps = 3 * self.n_replicas
+        p.machrep.mean_up_time = self.meanUpTime; p.machrep.mean_repair_time = self.meanRepairTime
+        p.machrep.delta = self.delta; p.machrep.seed1 = self.seeds[0]; p.machrep.seed2 = self.seeds[1]
+        p.machrep.seed_stride = self.seed_stride
+
+
+@dataclass
+class LogicalProcessState:
+    lpStateId: int
+    lpStateLocalTime: float
+    lpStateEventQueueTime: float
+    lpStateEventQueueSize: int
+    lpStateLogSize: int
+    lpStateInputMessageCount: int
+    lpStateOutputMessageCount: int
+    lpStateRollbackCount: int
+
+
+def make_params(model, ps: DIOParams, specs: Specs, rank=0, world=1, device=-1, nccl_id=None):
+    p = ffi.tw_params()
+    model.fill(p)
+    p.rank = rank; p.world = world; p.device = device
+    p.queue_capacity = ps.queueCapacity; p.max_events_per_step = ps.maxEventsPerStep
+    p.steps_per_launch = ps.stepsPerLaunch; p.proc_limit = ps.procLimit; p.fossil_threshold = ps.fossilThreshold
+    p.start_time = specs.spcStartTime; p.stop_time = specs.spcStopTime
+    p.time_horizon = -1.0 if ps.dioTimeHorizon is None else float(ps.dioTimeHorizon)
+    if nccl_id is not None:
+        C.memmove(p.nccl_id, bytes(nccl_id), 128)
+    return p
+
+
+class DIO:
+    """A batch of logical processes living on one GPU partition (the device-side `EventQueue DIO`s)."""
+
+    def __init__(self, model, ps: DIOParams = defaultDIOParams, specs: Specs = Specs(), rank=0, world=1, device=-1,
+                 nccl_id=None):
+        self.lib = ffi.load()
+        self.model, self.ps, self.specs = model, ps, specs
+        self.params = make_params(model, ps, specs, rank, world, device, nccl_id)
+        h = C.c_void_p()
+        rc = self.lib.tw_create(C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise SimulationAbort(rc, self.lib.tw_last_error(None).decode())
+        self.h = h
+        base, n = C.c_uint32(), C.c_uint32()
+        self.lib.tw_partition(self.h, C.byref(base), C.byref(n))
+        self.lp_base, self.n_local = base.value, n.value
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tw_destroy(self.h); self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SimulationAbort(rc, self.lib.tw_last_error(self.h).decode())
+
+    def reset(self):
+        self._check(self.lib.tw_reset(self.h))
+
+    # -- messages
+    def initialEvents(self, out=None):
+        """Synthetic start-time messages addressed to this partition's LPs, as a host record array.
+
+        `out` may be a preallocated (e.g. pinned) EVENT_DTYPE array; otherwise a numpy array is allocated."""
+        per_lp = self.model.population if isinstance(self.model, PHOLD) else 1
+        cap = max(1, self.n_local * per_lp)
+        buf = np.zeros(cap, dtype=EVENT_DTYPE) if out is None else out
+        assert buf.dtype == EVENT_DTYPE and len(buf) >= cap
+        n = C.c_size_t()
+        rc = self.lib.tw_model_initial_events_range(C.byref(self.params), self.lp_base, self.lp_base + self.n_local,
+                                                    buf.ctypes.data, len(buf), C.byref(n))
+        self._check(rc)
+        return buf[: n.value]
+
+    def enqueueMessages(self, events: np.ndarray):
+        """QueueMessageBulk: `events` is a host array of EVENT_DTYPE records."""
+        assert events.dtype == EVENT_DTYPE and events.flags["C_CONTIGUOUS"]
+        self._check(self.lib.tw_enqueue_messages(self.h, events.ctypes.data, len(events)))
+
+    def enqueueMessage(self, pid, t, src=None, send_time=None, ctr=0, msg_type=0, value=0.0):
+        """enqueueMessage pid t a (Optimistic/Message.hs:48-69), issued from the start time by the host."""
+        ev = ffi.tw_event()
+        ev.recv_ts = t; ev.send_ts = self.specs.spcStartTime if send_time is None else send_time
+        ev.ctr = ctr; ev.src = pid if src is None else src; ev.dst = pid; ev.type = msg_type; ev.value = value
+        self._check(self.lib.tw_enqueue_message(self.h, C.byref(ev)))
+
+    def sendMessage(self, pid, **kw):
+        """sendMessage pid a = enqueueMessage pid <now> a (Optimistic/Message.hs:41-45)."""
+        self.enqueueMessage(pid, self.globalTime(), **kw)
+
+    # -- running
+    def runEventInStopTime(self, until=None):
+        st = ffi.tw_run_stats()
+        t = self.specs.spcStopTime if until is None else until
+        self._check(self.lib.tw_run(self.h, t, C.byref(st)))
+        return st
+
+    def globalTime(self):
+        g = C.c_double()
+        self._check(self.lib.tw_gvt(self.h, C.byref(g)))
+        return g.value
+
+    def logicalProcessState(self, lp):
+        s = ffi.tw_lp_state()
+        self._check(self.lib.tw_lp_state_get(self.h, lp, C.byref(s)))
+        return LogicalProcessState(s.lp, s.local_time, s.event_queue_time, s.event_queue_size, s.log_size,
+                                   s.input_message_count, s.output_message_count, s.rollback_count)
+
+    # -- results
+    def lpStats(self):
+        n_exec = np.zeros(self.n_local, dtype=np.uint64); h = np.zeros(self.n_local, dtype=np.uint64)
+        self._check(self.lib.tw_read_lp_stats(self.h, n_exec.ctypes.data, h.ctypes.data, self.n_local))
+        return n_exec, h
+
+    def machRepResults(self):
+        first_master = ((self.lp_base + 2) // 3) * 3
+        end = self.lp_base + self.n_local
+        n = max(0, (end - first_master + 2) // 3) if first_master < end else 0
+        out = np.zeros(n, dtype=MACHREP_DTYPE)
+        if n:
+            self._check(self.lib.tw_read_machrep(self.h, out.ctypes.data, n))
+        return out
+
+
+EVENT_DTYPE = np.dtype([("recv_ts", "<f8"), ("send_ts", "<f8"), ("ctr", "<u8"), ("src", "<u4"), ("dst", "<u4"),
+                        ("type", "<u4"), ("pad", "<u4"), ("value", "<f8")])
+MACHREP_DTYPE = np.dtype([("total_up_time", "<f8"), ("n_rep", "<i8"), ("n_immed_rep", "<i8"),
+                          ("up_time_prop", "<f8"), ("immed_prop", "<f8")])
+assert EVENT_DTYPE.itemsize == C.sizeof(ffi.tw_event) == 48
+assert MACHREP_DTYPE.itemsize == C.sizeof(ffi.tw_machrep_result) == 40
+
+
+def runDIO(model, ps: DIOParams = defaultDIOParams, timeServerId: Optional[TimeServer] = None, specs: Specs = Specs(),
+           **partition):
+    """runDIO m ps timeServerId (Internal/DIO.hs:327-328): returns (dio, simulation).
+
+    `simulation()` registers with the time server, loads the model's start-time messages, runs to the stop time
+    (runEventInStopTime) and returns (run statistics, per-LP committed counts, per-LP trace hashes[, MachRep2 results]).
+    """
+    dio = DIO(model, ps, specs, **partition)
+    if timeServerId is not None:
+        timeServerId._dio = dio
+
+    def simulation():
+        dio.enqueueMessages(dio.initialEvents())
+        st = dio.runEventInStopTime()
+        n_exec, h = dio.lpStats()
+        if isinstance(model, MachRep2):
+            return st, n_exec, h, dio.machRepResults()
+        return st, n_exec, h
+
+    return dio, simulation

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- committed events/sec of the Time Warp hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--workload c4|c3|c5|c2] [--impl reference]
+
+A "step" is one complete run of the synthetic workload (load the start-time messages, advance until GVT passes
+the stop time, read the per-LP results).  `value` is device-timed (CUDA events inside tw_run, inputs resident in
+HBM); `e2e` is the same metric through the public API with HOST buffers (pinned host -> device copy of the
+start-time messages and device -> host read of the per-LP results inside the timed region).
+For N > 1 launch with torchrun: one rank per GPU, the LP range is sharded, messages to remote LPs are NVLink
+peer stores from inside the step kernel and GVT is an ncclAllReduce(min).
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, kind "port"; the Haskell engine
+itself cannot be built in this image: no GHC) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALGO_BYTES_PHOLD = 208      # bytes per committed PHOLD event
+ALGO_BYTES_MACHREP = 288
+
+WORKLOADS = {
+    # name: (description, model kwargs, stop, default horizon, capacity, cpu-sample stop)
+    "c4": dict(desc="PHOLD 1M LPs, 50% remote, P=16, lookahead 0.1, exp(1) delays, T=20 (BASELINE configs[3])",
+               kind="phold", n_lps=1 << 20, remote_pct=50, stop=20.0, horizon=0.4, cap=128, cpu_stop=0.5),
+    "c3": dict(desc="PHOLD 64K LPs, 10% remote, P=16, lookahead 0.1, exp(1) delays, T=100 (BASELINE configs[2])",
+               kind="phold", n_lps=1 << 16, remote_pct=10, stop=100.0, horizon=0.4, cap=128, cpu_stop=10.0),
+    "c5": dict(desc="rollback-heavy PHOLD 256K LPs, 50% remote, 10% of the remote messages to 4096 hot LPs "
+                    "(each hot LP holds ~7x the average event population), horizon 0.5, T=20 (BASELINE configs[4])",
+               kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10, stop=20.0, horizon=0.5, cap=512,
+               cpu_stop=2.0),
+    "c2": dict(desc="MachRep2DistributedReproducible replicated as 4096 independent 3-LP groups, stop 1000 (BASELINE configs[1])",
+               kind="machrep", n_replicas=4096, stop=1000.0, horizon=-1.0, cap=64, cpu_stop=1000.0),
+}
+
+
+def load_pkg():
+    import importlib.util
+    name = "aivika_distributed_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    d = os.path.join(ROOT, "aivika-distributed_b200")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def oracle_sample(wl, args):
+    """CPU baseline on a bounded sample of the same workload: the sequential oracle (1 core)."""
+    import helpers as H
+    t_init = 0.0
+    if wl["kind"] == "phold":
+        p = H.phold_params(wl["n_lps"], wl["cpu_stop"], remote_pct=wl["remote_pct"], n_hot=wl.get("n_hot", 0),
+                           hot_pct=wl.get("hot_pct", 0), seed=args.seed)
+        p0 = H.phold_params(wl["n_lps"], -1.0, remote_pct=wl["remote_pct"], n_hot=wl.get("n_hot", 0),
+                            hot_pct=wl.get("hot_pct", 0), seed=args.seed)
+        t = time.perf_counter(); H.oracle_phold(p0); t_init = time.perf_counter() - t      # population set-up only
+        t = time.perf_counter(); _, _, s = H.oracle_phold(p); dt = time.perf_counter() - t
+        n = s.committed
+        sample = f"same workload truncated to stop time {wl['cpu_stop']} ({n} events), population set-up ({t_init:.1f} s) subtracted"
+    else:
+        nrep = min(wl["n_replicas"], 512)
+        p = H.machrep_params(nrep, wl["cpu_stop"])
+        t = time.perf_counter(); res = H.oracle_machrep(p); dt = time.perf_counter() - t
+        n = sum(sum(r.n_exec) for r in res)
+        sample = f"first {nrep} replicas of the same workload ({n} events)"
+    return n / max(dt - t_init, 1e-9), sample
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, sample = oracle_sample(wl, args)
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "committed events/sec", "value": v, "unit": "events/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": 1, "kind": "port",
+                         "sample": sample + "; sequential DES restatement (oracle/oracle.c); the Haskell reference "
+                                            "cannot be built here (no GHC)"},
+        "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--horizon", type=float, default=None)
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--cap", type=int, default=None)
+    ap.add_argument("--stop", type=float, default=None)
+    ap.add_argument("--steps-per-launch", type=int, default=16)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.stop is not None:
+        wl["stop"] = args.stop
+    if args.horizon is not None:
+        wl["horizon"] = args.horizon
+    if args.cap is not None:
+        wl["cap"] = args.cap
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = load_pkg()
+    from aivika_distributed_b200 import dio as D
+    lib = pkg._ffi.load()
+
+    nccl_id = None
+    if world > 1:
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            assert lib.tw_nccl_unique_id(C.byref(buf)) == 0
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        nccl_id = bytes(t.cpu().tolist())
+
+    if wl["kind"] == "phold":
+        model = D.PHOLD(n_lps=wl["n_lps"], population=16, remote_pct=wl["remote_pct"], lookahead=0.1, mean=1.0,
+                        seed=args.seed, n_hot=wl.get("n_hot", 0), hot_pct=wl.get("hot_pct", 0))
+        algo_bytes = ALGO_BYTES_PHOLD
+    else:
+        model = D.MachRep2(n_replicas=wl["n_replicas"])
+        algo_bytes = ALGO_BYTES_MACHREP
+    ps = D.DIOParams(dioTimeHorizon=None if wl["horizon"] < 0 else wl["horizon"], queueCapacity=wl["cap"],
+                     maxEventsPerStep=args.batch, stepsPerLaunch=args.steps_per_launch)
+    specs = D.Specs(0.0, wl["stop"])
+    dio = D.DIO(model, ps, specs, rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
+
+    # synthetic start-time messages in PINNED host memory (torch is only the allocator here)
+    per_lp = 16 if wl["kind"] == "phold" else 1
+    n_init_cap = max(1, dio.n_local * per_lp)
+    pinned = torch.empty(n_init_cap * 48, dtype=torch.uint8).pin_memory()
+    ev_view = pinned.numpy().view(D.EVENT_DTYPE)
+    events = dio.initialEvents(out=ev_view)
+    h2d = int(events.nbytes); d2h = int(dio.n_local * 16 + C.sizeof(pkg._ffi.tw_run_stats))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    dev_ms, e2e_s, committed, hashes, stats = [], [], [], [], []
+    launches0 = None
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            sampler.start()
+            launches0 = lib.tw_kernel_launch_count()
+        dio.reset()
+        barrier()
+        t0 = time.perf_counter()
+        dio.enqueueMessages(events)            # pinned host -> device + k_route
+        st = dio.runEventInStopTime()          # the timed device region (CUDA events inside tw_run)
+        n_exec, h = dio.lpStats()              # device -> host
+        t1 = time.perf_counter()
+        barrier()
+        if i >= args.warmup:
+            dev_ms.append(st.device_ms); e2e_s.append(t1 - t0); committed.append(int(st.committed))
+            hashes.append(int(st.trace_hash_sum)); stats.append(st.as_dict())
+            assert int(n_exec.sum()) == int(st.committed)
+    launches = lib.tw_kernel_launch_count() - launches0
+    sampler.stop_flag = True
+    if sampler.is_alive():
+        sampler.join(timeout=2)
+    assert len(set(committed)) == 1 and len(set(hashes)) == 1, "the committed trace must not depend on the run"
+
+    # max over ranks of the per-step device time, sum over ranks of the committed events
+    tms = torch.tensor(dev_ms, dtype=torch.float64, device="cuda")
+    te2e = torch.tensor(e2e_s, dtype=torch.float64, device="cuda")
+    tcm = torch.tensor([committed[0], stats[-1]["executed"], stats[-1]["rolled_back"], stats[-1]["anti_sent"],
+                        stats[-1]["sent_remote"], stats[-1]["sent_local"], launches, hashes[0] & ((1 << 62) - 1)],
+                       dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX); dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tcm, op=dist.ReduceOp.SUM)
+    total_ms = float(tms.sum()); total_e2e = float(te2e.sum())
+    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, _ = [int(x) for x in tcm.tolist()]
+    K = args.steps
+    value = tot_committed * K / (total_ms / 1e3)
+    e2e_value = tot_committed * K / total_e2e
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        steps_per_run = stats[-1]["steps"]
+        achieved = (tot_committed / world) * algo_bytes * K / (total_ms / 1e3) / 1e9
+        line = {
+            "metric": "committed events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "time_horizon": wl["horizon"],
+                       "max_events_per_lp_per_superstep": args.batch, "queue_capacity": wl["cap"],
+                       "parallelism": f"lp-sharding x{world}",
+                       "l2": "per-LP event rings (n_lps x capacity x 32 B) exceed the 126 MB L2 for c4/c5; c3's live set is L2-resident"},
+            "committed_events_per_step": tot_committed, "executed_events_per_step": tot_exec,
+            "rollback_efficiency": tot_committed / max(1, tot_exec),
+            "rolled_back_per_step": tot_rb, "anti_messages_per_step": tot_anti,
+            "remote_messages_per_step": tot_remote, "local_messages_per_step": tot_local,
+            "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(hashes[0]),
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": tot_launch,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None,
+                         "note": f"k_step: {algo_bytes} algorithmic B per committed event (SURVEY.md 8d) x "
+                                 f"{tot_committed / world / max(1, steps_per_run):.0f} events per launch, "
+                                 f"{total_ms / K / max(1, steps_per_run) * 1e3:.2f} us per launch; peak = measured copy bandwidth"
+                                 + ("" if peaks else " (fallback)")},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, sample = oracle_sample(wl, args)
+            line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": 1, "kind": "port",
+                                    "sample": sample + "; sequential DES restatement (oracle/oracle.c)"}
+        print(json.dumps(line), flush=True)
+    dio.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

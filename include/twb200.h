@@ -189,6 +189,9 @@ int tw_partition(const tw_engine *e, uint32_t *lp_base, uint32_t *n_local);
  * PHOLD initial population (n_lps*population events) / MachRep2 START events (2 per replica).
  * Writes at most cap events, returns the count in *n. */
 int tw_model_initial_events(const tw_params *params, tw_event *out, size_t cap, size_t *n);
+/* Same, restricted to the start-time messages addressed to LPs lp_begin <= lp < lp_end (a rank's slice). */
+int tw_model_initial_events_range(const tw_params *params, uint32_t lp_begin, uint32_t lp_end,
+                                  tw_event *out, size_t cap, size_t *n);
 
 /* ncclGetUniqueId for multi-GPU runs; rank 0 calls it and distributes the 128 bytes. */
 int tw_nccl_unique_id(uint8_t out[128]);

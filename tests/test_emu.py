@@ -1,0 +1,92 @@
+"""Host-side logic of the engine: the device functions of tw_core.cuh compiled for the CPU (tests/emu) and run
+LP by LP in shuffled order must commit exactly the sequential oracle's schedule for every horizon, batch size,
+capacity and partitioning.  This is a debugging aid for the rollback / annihilation / GVT logic; the parity
+claim for the product is made by the `-m gpu` tests through the C ABI."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+
+def check_phold(H, p, seeds=(0, 1)):
+    n_exec, h, s = H.oracle_phold(p)
+    out = None
+    for sd in seeds:
+        rc, e_exec, e_hash, _, stats = H.emu_run(p, sd)
+        assert rc == 0
+        assert (e_exec == n_exec).all() and (e_hash == h).all()
+        assert stats.committed == s.committed
+        assert stats.executed - stats.rolled_back == stats.committed
+        out = stats
+    return out
+
+
+@pytest.mark.parametrize("horizon", [0.1, 0.5, 2.0, -1.0])
+@pytest.mark.parametrize("batch", [1, 4])
+def test_phold_all_horizons_commit_the_sequential_schedule(H, horizon, batch):
+    st_ = check_phold(H, H.phold_params(300, 6.0, remote_pct=40, horizon=horizon, batch=batch))
+    if horizon == 0.1:
+        assert st_.rolled_back == 0 and st_.anti_sent == 0      # window == lookahead is conservative
+    if horizon != 0.1:
+        assert st_.rolled_back > 0 and st_.anti_sent == st_.annihilated
+
+
+def test_phold_edge_shapes(H):
+    check_phold(H, H.phold_params(1, 30.0, remote_pct=100, population=3))          # single LP: never remote
+    check_phold(H, H.phold_params(2, 30.0, remote_pct=100, population=1, horizon=-1.0))
+    check_phold(H, H.phold_params(64, 4.0, remote_pct=0))                          # no remote messages at all
+    check_phold(H, H.phold_params(64, 0.0, remote_pct=50))                         # nothing before the stop time
+    check_phold(H, H.phold_params(129, 5.0, remote_pct=100, lookahead=0.0, horizon=-1.0))   # zero lookahead
+
+
+def test_phold_skewed_fanout_and_small_ring(H):
+    st_ = check_phold(H, H.phold_params(512, 5.0, remote_pct=50, n_hot=64, hot_pct=30, horizon=1.0, cap=256))
+    assert st_.rolled_back > 0
+    # tiny ring: optimism stalls on proc_limit and tombstones are compacted, results must not change
+    check_phold(H, H.phold_params(64, 6.0, remote_pct=50, population=4, horizon=-1.0, cap=64, proc_limit=4, fossil=2))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_phold_partitioned(H, world):
+    st_ = check_phold(H, H.phold_params(500, 5.0, remote_pct=50, horizon=0.7, world=world), seeds=(3,))
+    assert st_.sent_remote > 0
+
+
+def test_queue_overflow_is_reported_not_silent(H):
+    rc, *_ = H.emu_run(H.phold_params(64, 50.0, remote_pct=50, population=16, horizon=-1.0, cap=16), 1)
+    assert rc == 5   # TW_ERR_QUEUE_OVERFLOW
+
+
+def check_machrep(H, p, seeds=(0, 5)):
+    res = H.oracle_machrep(p)
+    for sd in seeds:
+        rc, n_exec, h, mr, stats = H.emu_run(p, sd)
+        assert rc == 0
+        for r in range(p.n_lps // 3):
+            o, m = res[r], mr[r]
+            assert (o.total_up_time, o.n_rep, o.n_immed_rep) == (m.total_up_time, m.n_rep, m.n_immed_rep)
+            assert o.up_time_prop == m.up_time_prop and o.immed_prop == m.immed_prop     # bit-exact, stricter than 1e-9
+            assert [o.n_exec[k] for k in range(3)] == [int(n_exec[3 * r + k]) for k in range(3)]
+            assert [o.hash[k] for k in range(3)] == [int(h[3 * r + k]) for k in range(3)]
+    return stats
+
+
+def test_machrep2_reference_configuration_unbounded_optimism(H):
+    st_ = check_machrep(H, H.machrep_params(1, 1000.0))       # dioTimeHorizon = Nothing, as in the reference program
+    assert st_.rolled_back > 0
+
+
+@pytest.mark.parametrize("horizon,batch", [(100.0, 4), (1.0, 1), (0.0, 4)])
+def test_machrep2_horizons(H, horizon, batch):
+    check_machrep(H, H.machrep_params(6, 150.0, horizon=horizon, batch=batch), seeds=(2,))
+
+
+def test_machrep2_partitioned_keeps_replicas_whole(H):
+    check_machrep(H, H.machrep_params(7, 100.0, horizon=5.0, world=3), seeds=(1,))
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(2, 200), pop=st.integers(1, 6), rp=st.integers(0, 100), hor=st.sampled_from([0.05, 0.3, 1.5, -1.0]),
+       batch=st.integers(1, 4), seed=st.integers(0, 2 ** 32), world=st.sampled_from([1, 2, 4]), shuffle=st.integers(0, 99))
+def test_phold_random_configurations(H, n, pop, rp, hor, batch, seed, world, shuffle):
+    p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hor, batch=batch, seed=seed, world=world, cap=128)
+    check_phold(H, p, seeds=(shuffle,))
