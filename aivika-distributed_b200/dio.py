@@ -281,3 +281,41 @@ def runDIO(model, ps: DIOParams = defaultDIOParams, timeServerId: Optional[TimeS
         return st, n_exec, h
 
     return dio, simulation
+
+
+# ---------------------------------------------------------------- multi-rank host logic (one process per GPU)
+def partition_range(model, rank, world):
+    """LP range [lo, hi) owned by `rank`: contiguous blocks of ceil(n/world) LPs, MachRep2 replicas kept whole.
+    Must agree with Engine::init in csrc/engine.cu (checked by tests on both sides)."""
+    n = model.n_lps if isinstance(model, PHOLD) else 3 * model.n_replicas
+    n_per = (n + world - 1) // world
+    if isinstance(model, MachRep2) and world > 1:
+        n_per = ((n_per + 2) // 3) * 3
+    lo = min(n, n_per * rank)
+    return lo, min(n, lo + n_per)
+
+
+def share_nccl_id(dist, rank, device=None):
+    """Rank 0 creates the ncclUniqueId (tw_nccl_unique_id) and broadcasts its 128 bytes over torch.distributed."""
+    import torch
+    buf = (C.c_uint8 * 128)()
+    if rank == 0:
+        rc = ffi.load().tw_nccl_unique_id(C.byref(buf))
+        if rc != 0:
+            raise SimulationAbort(rc, "ncclGetUniqueId failed")
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=device or "cpu")
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().tolist())
+
+
+def reduce_run(dist, world, device_ms, e2e_s, counters, device=None):
+    """bench.py's cross-rank reduction: MAX over ranks of the per-step times, SUM of the event counters."""
+    import torch
+    tms = torch.tensor(device_ms, dtype=torch.float64, device=device or "cpu")
+    te2e = torch.tensor(e2e_s, dtype=torch.float64, device=device or "cpu")
+    tcm = torch.tensor(counters, dtype=torch.int64, device=device or "cpu")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tcm, op=dist.ReduceOp.SUM)
+    return tms.tolist(), te2e.tolist(), [int(x) for x in tcm.tolist()]

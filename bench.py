@@ -191,15 +191,7 @@ def main():
     pkg = load_pkg()
     from aivika_distributed_b200 import dio as D
     lib = pkg._ffi.load()
-
-    nccl_id = None
-    if world > 1:
-        buf = (C.c_uint8 * 128)()
-        if rank == 0:
-            assert lib.tw_nccl_unique_id(C.byref(buf)) == 0
-        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        nccl_id = bytes(t.cpu().tolist())
+    nccl_id = D.share_nccl_id(dist, rank, device="cuda") if world > 1 else None
 
     if wl["kind"] == "phold":
         model = D.PHOLD(n_lps=wl["n_lps"], population=16, remote_pct=wl["remote_pct"], lookahead=0.1, mean=1.0,
@@ -253,16 +245,12 @@ def main():
     assert len(set(committed)) == 1 and len(set(hashes)) == 1, "the committed trace must not depend on the run"
 
     # max over ranks of the per-step device time, sum over ranks of the committed events
-    tms = torch.tensor(dev_ms, dtype=torch.float64, device="cuda")
-    te2e = torch.tensor(e2e_s, dtype=torch.float64, device="cuda")
-    tcm = torch.tensor([committed[0], stats[-1]["executed"], stats[-1]["rolled_back"], stats[-1]["anti_sent"],
-                        stats[-1]["sent_remote"], stats[-1]["sent_local"], launches, hashes[0] & ((1 << 62) - 1)],
-                       dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX); dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tcm, op=dist.ReduceOp.SUM)
-    total_ms = float(tms.sum()); total_e2e = float(te2e.sum())
-    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, _ = [int(x) for x in tcm.tolist()]
+    ms_l, e2e_l, cnt = D.reduce_run(dist, world, dev_ms, e2e_s,
+                                    [committed[0], stats[-1]["executed"], stats[-1]["rolled_back"], stats[-1]["anti_sent"],
+                                     stats[-1]["sent_remote"], stats[-1]["sent_local"], launches,
+                                     hashes[0] & ((1 << 62) - 1)], device="cuda")
+    total_ms = float(sum(ms_l)); total_e2e = float(sum(e2e_l))
+    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, _ = cnt
     K = args.steps
     value = tot_committed * K / (total_ms / 1e3)
     e2e_value = tot_committed * K / total_e2e
