@@ -59,7 +59,7 @@ def test_phold_golden_fixture(H):
     import json, os
     g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "phold_small.json")))
     for case in g["cases"]:
-        p = H.phold_params(horizon=0.6, **case["params"])
+        p = H.phold_params(horizon=0.6, cap=1024, **case["params"])
         st, n_exec, h = run_phold(H, p)
         assert int(st.committed) == case["committed"] and hex(int(st.trace_hash_sum)) == case["hash_sum"]
         assert [int(x) for x in n_exec[:8]] == case["n_exec_head"]
