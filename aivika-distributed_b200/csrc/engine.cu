@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const Dev<M> d)
     if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
-    if (l < d.n_local) lp_step<M>(d, acc, l, gvt, wend, step & 1u);
+    lp_step<M>(d, acc, l, gvt, wend, step & 1u);       // all lanes enter: phases reconverge inside
     if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
     block_finish(ctl, acc, step, d.world, true);
 }
