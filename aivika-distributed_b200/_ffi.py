@@ -85,7 +85,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("TWB200_LIB") or LIB_PATH     # TWB200_LIB: tuning builds of the same CUDA library
     if not os.path.exists(p):
         raise OSError(f"{p} not found: build it with `make -C aivika-distributed_b200/csrc` "
                       f"(or __graft_entry__.build()); this engine has no CPU fallback")

@@ -26,7 +26,13 @@
 
 namespace twb {
 
-constexpr int kBlock = 128;
+#ifndef TW_BLOCK
+#define TW_BLOCK 128
+#endif
+#ifndef TW_MINBLOCKS
+#define TW_MINBLOCKS 4
+#endif
+constexpr int kBlock = TW_BLOCK;
 static std::atomic<uint64_t> g_launches{0};
 
 // ------------------------------------------------------------------ device helpers
@@ -94,7 +100,7 @@ __device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t 
 }
 
 template <class M>
-__global__ void __launch_bounds__(kBlock) k_step(const Dev<M> d)
+__global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const Dev<M> d)
 {
     Ctl *ctl = d.ctl;
     const double gvt = *(volatile double *)&ctl->gvt;
