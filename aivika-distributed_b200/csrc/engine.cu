@@ -26,11 +26,12 @@
 
 namespace twb {
 
+// Launch shape of k_step, chosen by the sweep in profiles/r1_tuning.md (tools/sweep_variants.sh)
 #ifndef TW_BLOCK
-#define TW_BLOCK 128
+#define TW_BLOCK 256
 #endif
 #ifndef TW_MINBLOCKS
-#define TW_MINBLOCKS 4
+#define TW_MINBLOCKS 2
 #endif
 constexpr int kBlock = TW_BLOCK;
 static std::atomic<uint64_t> g_launches{0};
@@ -100,7 +101,7 @@ __device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t 
 }
 
 template <class M>
-__global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const Dev<M> d)
+__global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_constant__ Dev<M> d)
 {
     Ctl *ctl = d.ctl;
     const double gvt = *(volatile double *)&ctl->gvt;
@@ -111,7 +112,10 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const Dev<M> d)
     if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
-    lp_step<M>(d, acc, l, gvt, wend, step & 1u);       // all lanes enter: phases reconverge inside
+    extern __shared__ uint4 tw_stage_smem[];             // per warp: kStage entries x G granules x 32 lanes x 16 B
+    Stage<M> stg;
+    stg.base = tw_stage_smem + (threadIdx.x >> 5) * (M::kStage * Stage<M>::G * 32) + (threadIdx.x & 31);
+    lp_step<M>(d, acc, stg, l, gvt, wend, step & 1u);  // all lanes enter: phases reconverge inside
     if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
     block_finish(ctl, acc, step, d.world, true);
 }
@@ -344,12 +348,15 @@ struct Engine : EngineBase {
         TW_CUDA(cudaMalloc(&d_tmp, 2 * sizeof(unsigned long long)));
         TW_CUDA(cudaHostAlloc(&h_ctl, 2 * sizeof(Ctl), cudaHostAllocDefault));
         grid = (int)((nl + kBlock - 1) / kBlock);
+        TW_CUDA(cudaFuncSetAttribute(k_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
         d.peer_pages[d.rank] = d.pages; d.peer_in[d.rank] = d.in;
         if (p.world > 1) { int rc = init_peers(); if (rc) return rc; }
         return reset();
     }
 
     // exchange cudaIpc handles of pages / inbox counters through NCCL and map every peer (NVLink P2P)
+    static size_t stage_bytes() { return (size_t)(kBlock / 32) * M::kStage * Stage<M>::G * 32 * sizeof(uint4); }
+
     int init_peers()
     {
         if (!g_nccl.load(err)) return TW_ERR_CUDA;
@@ -433,7 +440,7 @@ struct Engine : EngineBase {
         cudaGraph_t g = nullptr;
         TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         for (uint32_t i = 0; i < steps; ++i) {
-            k_step<M><<<grid, kBlock, 0, stream>>>(d);
+            k_step<M><<<grid, kBlock, stage_bytes(), stream>>>(d);
             if (P.world > 1) {
                 int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);
                 if (e) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); err = "ncclAllReduce failed during capture"; return TW_ERR_CUDA; }

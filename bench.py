@@ -31,9 +31,9 @@ ALGO_BYTES_MACHREP = 288
 WORKLOADS = {
     # name: (description, model kwargs, stop, default horizon, capacity, cpu-sample stop)
     "c4": dict(desc="PHOLD 1M LPs, 50% remote, P=16, lookahead 0.1, exp(1) delays, T=20 (BASELINE configs[3])",
-               kind="phold", n_lps=1 << 20, remote_pct=50, stop=20.0, horizon=0.4, cap=128, cpu_stop=0.5),
+               kind="phold", n_lps=1 << 20, remote_pct=50, stop=20.0, horizon=0.2, cap=128, cpu_stop=0.5),
     "c3": dict(desc="PHOLD 64K LPs, 10% remote, P=16, lookahead 0.1, exp(1) delays, T=100 (BASELINE configs[2])",
-               kind="phold", n_lps=1 << 16, remote_pct=10, stop=100.0, horizon=0.4, cap=128, cpu_stop=10.0),
+               kind="phold", n_lps=1 << 16, remote_pct=10, stop=100.0, horizon=0.2, cap=128, cpu_stop=10.0),
     "c5": dict(desc="rollback-heavy PHOLD 256K LPs, 50% remote, 10% of the remote messages to 4096 hot LPs "
                     "(each hot LP holds ~7x the average event population), horizon 0.5, T=20 (BASELINE configs[4])",
                kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10, stop=20.0, horizon=0.5, cap=512,

@@ -80,7 +80,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
         if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
         acc.init();
-        for (auto &o : order) lp_step<M>(parts[o.first].d, acc, o.second, gvt, wend, step & 1u);
+        for (auto &o : order) { Stage<M> stg; lp_step<M>(parts[o.first].d, acc, stg, o.second, gvt, wend, step & 1u); }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
         const double g = std::min(acc.pend_min, acc.emit_min);
         if (g < gvt) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", gvt, g, step); return 100; }
@@ -90,6 +90,12 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         S.anti_sent += acc.anti; S.annihilated += acc.annih; S.retries += acc.retry; S.sent_local += acc.sent_local; S.sent_remote += acc.sent_remote;
     }
     S.gvt = gvt;
+    // anti-messages sent in the final steps can still sit unconsumed in inboxes (their twins lie beyond the stop time);
+    // reported through the otherwise unused kernel_launches field so tests can close the balance anti_sent == annihilated + left
+    for (uint32_t r = 0; r < W; ++r)
+        for (uint32_t l = 0; l < parts[r].d.n_local; ++l)
+            for (uint32_t a = parts[r].hdr[l].consumed; a != parts[r].in[l].total; ++a)
+                if (parts[r].pages[(size_t)l * cap + (a & (cap - 1))].ctr & kAntiBit) S.kernel_launches++;
     for (uint32_t r = 0; r < W; ++r)
         for (uint32_t l = 0; l < parts[r].d.n_local; ++l) {
             const uint32_t lp = parts[r].d.lp_base + l;

@@ -1,4 +1,4 @@
-for f in aivika-distributed_b200/csrc/libtwb200.so aivika-distributed_b200/csrc/variants/*.so; do
+for f in aivika-distributed_b200/csrc/variants/*.so; do
   for w in "c3 --stop 30" "c4 --stop 5"; do
     TWB200_LIB=$PWD/$f python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
 import sys,json
