@@ -248,9 +248,10 @@ def main():
     ms_l, e2e_l, cnt = D.reduce_run(dist, world, dev_ms, e2e_s,
                                     [committed[0], stats[-1]["executed"], stats[-1]["rolled_back"], stats[-1]["anti_sent"],
                                      stats[-1]["sent_remote"], stats[-1]["sent_local"], launches,
-                                     hashes[0] & ((1 << 62) - 1)], device="cuda")
+                                     hashes[0] & 0xFFFFFFFF, hashes[0] >> 32], device="cuda")
     total_ms = float(sum(ms_l)); total_e2e = float(sum(e2e_l))
-    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, _ = cnt
+    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, h_lo, h_hi = cnt
+    trace_hash_total = ((h_hi << 32) + h_lo) & ((1 << 64) - 1)       # sum over all LPs of the box, mod 2^64
     K = args.steps
     value = tot_committed * K / (total_ms / 1e3)
     e2e_value = tot_committed * K / total_e2e
@@ -276,7 +277,7 @@ def main():
             "rollback_efficiency": tot_committed / max(1, tot_exec),
             "rolled_back_per_step": tot_rb, "anti_messages_per_step": tot_anti,
             "remote_messages_per_step": tot_remote, "local_messages_per_step": tot_local,
-            "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(hashes[0]),
+            "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(trace_hash_total),
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": tot_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
