@@ -106,46 +106,52 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def oracle_sample(wl, args):
-    """CPU baseline on a bounded sample of the same workload: the sequential oracle (1 core)."""
+def cpu_sample(wl, args):
+    """CPU baseline on a bounded sample of the same workload: the multi-threaded Time Warp restatement of the
+    reference algorithm (oracle/tw_ref.cpp) on all host threads.  Returns (events/s, threads, sample description)."""
     import helpers as H
-    t_init = 0.0
+    threads = H.twref().twref_hardware_threads()
+    hz = wl["horizon"]
     if wl["kind"] == "phold":
-        p = H.phold_params(wl["n_lps"], wl["cpu_stop"], remote_pct=wl["remote_pct"], n_hot=wl.get("n_hot", 0),
-                           hot_pct=wl.get("hot_pct", 0), seed=args.seed)
-        p0 = H.phold_params(wl["n_lps"], -1.0, remote_pct=wl["remote_pct"], n_hot=wl.get("n_hot", 0),
-                            hot_pct=wl.get("hot_pct", 0), seed=args.seed)
-        t = time.perf_counter(); H.oracle_phold(p0); t_init = time.perf_counter() - t      # population set-up only
-        t = time.perf_counter(); _, _, s = H.oracle_phold(p); dt = time.perf_counter() - t
-        n = s.committed
-        sample = f"same workload truncated to stop time {wl['cpu_stop']} ({n} events), population set-up ({t_init:.1f} s) subtracted"
+        kw = dict(remote_pct=wl["remote_pct"], n_hot=wl.get("n_hot", 0), hot_pct=wl.get("hot_pct", 0), seed=args.seed, horizon=hz)
+        t = time.perf_counter(); H.twref_phold(H.phold_params(wl["n_lps"], -1.0, **kw), threads); t_init = time.perf_counter() - t
+        t = time.perf_counter(); rc, _, _, st = H.twref_phold(H.phold_params(wl["n_lps"], wl["cpu_stop"], **kw), threads)
+        dt = time.perf_counter() - t
+        assert rc == 0
+        n = st.committed
+        sample = (f"same workload truncated to stop time {wl['cpu_stop']} ({n} committed, {st.rolled_back} rolled back), "
+                  f"LP/population set-up ({t_init:.1f} s) subtracted")
     else:
         nrep = min(wl["n_replicas"], 512)
-        p = H.machrep_params(nrep, wl["cpu_stop"])
-        t = time.perf_counter(); res = H.oracle_machrep(p); dt = time.perf_counter() - t
-        n = sum(sum(r.n_exec) for r in res)
-        sample = f"first {nrep} replicas of the same workload ({n} events)"
-    return n / max(dt - t_init, 1e-9), sample
+        t_init = 0.0
+        t = time.perf_counter(); rc, _, _, _, st = H.twref_machrep(H.machrep_params(nrep, wl["cpu_stop"], horizon=hz), threads)
+        dt = time.perf_counter() - t
+        assert rc == 0
+        n = st.committed
+        sample = f"first {nrep} replicas of the same workload ({n} committed, {st.rolled_back} rolled back)"
+    cpu_sample.last_ms = (dt - t_init) * 1e3
+    desc = (sample + f"; C++ Time Warp restatement of the reference algorithm (oracle/tw_ref.cpp), {threads} threads; "
+            "the Haskell engine cannot be built here (no GHC)")
+    return n / max(dt - t_init, 1e-9), threads, desc
 
 
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     vals = []
-    sample = ""
+    sample, threads = "", 1
     for i in range(args.warmup + args.steps):
-        v, sample = oracle_sample(wl, args)
+        v, threads, sample = cpu_sample(wl, args)
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": "committed events/sec", "value": v, "unit": "events/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu_sample.last_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload},
-        "cpu_baseline": {"value": v, "unit": "events/s", "cores": 1, "kind": "port",
-                         "sample": sample + "; sequential DES restatement (oracle/oracle.c); the Haskell reference "
-                                            "cannot be built here (no GHC)"},
+        "config": {"workload": wl["desc"], "name": args.workload, "time_horizon": wl["horizon"],
+                   "max_events_per_lp_per_superstep": args.batch, "parallelism": f"{threads} host threads"},
+        "cpu_baseline": {"value": v, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -289,9 +295,8 @@ def main():
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, sample = oracle_sample(wl, args)
-            line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": 1, "kind": "port",
-                                    "sample": sample + "; sequential DES restatement (oracle/oracle.c)"}
+            v, threads, sample = cpu_sample(wl, args)
+            line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     dio.close()
     if world > 1:

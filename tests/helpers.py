@@ -160,3 +160,54 @@ def emu_run(p, shuffle_seed=1):
     st = ffi.tw_run_stats()
     rc = emu().emu_run(C.byref(p), shuffle_seed, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
     return rc, n_exec, h, mr, st
+
+
+# ------------------------------------------------------------------ CPU Time Warp restatement (oracle/tw_ref.cpp)
+class twref_stats(C.Structure):
+    _fields_ = [("committed", C.c_uint64), ("executed", C.c_uint64), ("rolled_back", C.c_uint64), ("rollbacks", C.c_uint64),
+                ("anti_sent", C.c_uint64), ("annihilated", C.c_uint64), ("stragglers", C.c_uint64), ("gvt_rounds", C.c_uint64),
+                ("gvt", C.c_double)]
+
+
+_twref = None
+
+
+def twref():
+    global _twref
+    if _twref is None:
+        d = os.path.join(ROOT, "oracle")
+        so = os.path.join(d, "libtwref.so")
+        if not os.path.exists(so) or os.path.getmtime(os.path.join(d, "tw_ref.cpp")) > os.path.getmtime(so):
+            _make(d, "libtwref.so")
+        L = C.CDLL(so)
+        L.twref_phold_run.argtypes = [C.POINTER(or_phold_params), C.c_int, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p,
+                                      C.POINTER(twref_stats)]
+        L.twref_machrep_run.argtypes = [C.POINTER(or_machrep_params), C.c_int, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.POINTER(twref_stats)]
+        L.twref_hardware_threads.restype = C.c_int
+        _twref = L
+    return _twref
+
+
+def twref_phold(p, threads, horizon=None, batch=4):
+    import numpy as np
+    op = or_phold_params(p.n_lps, p.phold.population, p.phold.lookahead, p.phold.mean, p.stop_time,
+                         p.phold.remote_pct, p.phold.n_hot, p.phold.hot_pct, 0, p.phold.seed)
+    n_exec = np.zeros(p.n_lps, dtype=np.uint64); h = np.zeros(p.n_lps, dtype=np.uint64)
+    st = twref_stats()
+    hz = p.time_horizon if horizon is None else horizon
+    rc = twref().twref_phold_run(C.byref(op), threads, hz, batch, n_exec.ctypes.data, h.ctypes.data, C.byref(st))
+    return rc, n_exec, h, st
+
+
+def twref_machrep(p, threads, horizon=None, batch=4):
+    import numpy as np
+    n_rep = p.n_lps // 3
+    op = or_machrep_params(n_rep, 0, p.machrep.mean_up_time, p.machrep.mean_repair_time, p.machrep.delta,
+                           p.stop_time, p.machrep.seed1, p.machrep.seed2, p.machrep.seed_stride)
+    n_exec = np.zeros(p.n_lps, dtype=np.uint64); h = np.zeros(p.n_lps, dtype=np.uint64)
+    res = (ffi.tw_machrep_result * n_rep)()
+    st = twref_stats()
+    hz = p.time_horizon if horizon is None else horizon
+    rc = twref().twref_machrep_run(C.byref(op), threads, hz, batch, n_exec.ctypes.data, h.ctypes.data, res, C.byref(st))
+    return rc, n_exec, h, res, st
