@@ -74,3 +74,23 @@ def test_invalid_arguments(H):
     p = H.machrep_params(1); p.n_lps = 4
     assert lib.tw_create(C.byref(p), C.byref(h)) == 1
     assert lib.tw_run(None, 1.0, None) == 1
+
+
+def test_haskell_binding_constants_match_the_abi(H):
+    """aivika-distributed_b200/hs/...B200.hs cannot be compiled here (no GHC); at least its struct sizes, the field
+    offsets it pokes and the imported symbols are checked against the real ABI."""
+    src = open(os.path.join(H.PKG_DIR, "hs", "Simulation", "Aivika", "Distributed", "Optimistic", "B200.hs")).read()
+    m = re.search(r"sizeofParams = (\d+); sizeofEvent = (\d+); sizeofRunStats = (\d+); sizeofMachRep = (\d+)", src)
+    f = H.ffi
+    assert [int(x) for x in m.groups()] == [C.sizeof(f.tw_params), C.sizeof(f.tw_event), C.sizeof(f.tw_run_stats), C.sizeof(f.tw_machrep_result)]
+    for sym in re.findall(r'foreign import ccall \w+ "(tw_\w+)"', src):
+        assert sym in f.EXPORTS
+    P = f.tw_params
+    expect = {"queueCapacity": P.queue_capacity.offset, "maxEventsPerStep": P.max_events_per_step.offset,
+              "stepsPerLaunch": P.steps_per_launch.offset, "spcStartTime": P.start_time.offset, "spcStopTime": P.stop_time.offset,
+              "pholdPopulation": P.phold.offset + f.tw_phold_params.population.offset,
+              "pholdSeed": P.phold.offset + f.tw_phold_params.seed.offset,
+              "mrMeanUpTime": P.machrep.offset + f.tw_machrep_params.mean_up_time.offset,
+              "mrSeedStride": P.machrep.offset + f.tw_machrep_params.seed_stride.offset}
+    for name, off in expect.items():
+        assert re.search(rf"pokeByteOff p {off}\s+{name}\b", src), (name, off)

@@ -192,3 +192,14 @@ def test_kernels_were_launched(H):
     before = lib.tw_kernel_launch_count()
     run_phold(H, H.phold_params(1000, 2.0))
     assert lib.tw_kernel_launch_count() > before
+
+
+def test_cpp_host_mirror_runs_machrep2(H):
+    """The C++ DIO mirror reproduces the reference program's result through the same C ABI."""
+    import os, subprocess
+    d = os.path.join(H.PKG_DIR, "host")
+    subprocess.run(["make", "-s", "-C", d, "example_machrep2"], check=True)
+    r = subprocess.run([os.path.join(d, "example_machrep2")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    o = H.oracle_machrep(H.machrep_params(1, 1000.0))[0]
+    assert f"({o.up_time_prop:.17g},{o.immed_prop:.17g})" in r.stdout

@@ -44,3 +44,15 @@ def test_initial_events_ranges_tile_the_population(H):
     buf = (H.ffi.tw_event * 16)()
     lib.tw_model_initial_events(C.byref(m), buf, 16, C.byref(n))
     assert n.value == 8 and [buf[i].dst for i in range(8)] == [1, 2, 4, 5, 7, 8, 10, 11]
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(H):
+    """aivika-distributed_b200/host/dio.hpp (C++ twin of the Haskell surface) builds against the C ABI; without a
+    GPU the example must abort with the engine's error, not fall back to anything."""
+    import os, subprocess, torch
+    d = os.path.join(H.PKG_DIR, "host")
+    subprocess.run(["make", "-s", "-C", d, "example_machrep2"], check=True)
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([os.path.join(d, "example_machrep2")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
