@@ -39,7 +39,7 @@ WORKLOADS = {
                kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10, stop=20.0, horizon=0.5, cap=512,
                cpu_stop=2.0),
     "c2": dict(desc="MachRep2DistributedReproducible replicated as 4096 independent 3-LP groups, stop 1000 (BASELINE configs[1])",
-               kind="machrep", n_replicas=4096, stop=1000.0, horizon=-1.0, cap=64, cpu_stop=1000.0),
+               kind="machrep", n_replicas=4096, stop=1000.0, horizon=2.0, cap=256, cpu_stop=1000.0),
 }
 
 
@@ -269,6 +269,11 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None        # DRAM bytes per k_step launch from the committed ncu --set full capture of this workload
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         steps_per_run = stats[-1]["steps"]
         achieved = (tot_committed / world) * algo_bytes * K / (total_ms / 1e3) / 1e9
         line = {
@@ -287,7 +292,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": tot_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None,
+                         "traffic": traffic,
                          "note": f"k_step: {algo_bytes} algorithmic B per committed event (SURVEY.md 8d) x "
                                  f"{tot_committed / world / max(1, steps_per_run):.0f} events per launch, "
                                  f"{total_ms / K / max(1, steps_per_run) * 1e3:.2f} us per launch; peak = measured copy bandwidth"
