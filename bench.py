@@ -291,6 +291,11 @@ def main():
             "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(trace_hash_total),
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": tot_launch,
+            "nvlink": None if world == 1 else {
+                "achieved_gbs_per_gpu": tot_remote * (32 if wl["kind"] == "phold" else 48) * K / (total_ms / 1e3) / 1e9 / world,
+                "peak_gbs_per_direction": 770.0,
+                "note": "32 B (PHOLD) / 48 B (MachRep2) per message whose destination LP lives on another GPU, written as "
+                        "peer stores from k_step; peak = measured peer copy (B200_PROFILING.md)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "note": f"k_step: {algo_bytes} algorithmic B per committed event (SURVEY.md 8d) x "
