@@ -25,7 +25,7 @@ ERROR_NAMES = {
 # every symbol include/twb200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
-    "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_model_initial_events", "tw_model_initial_events_range",
+    "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range",
     "tw_nccl_unique_id", "tw_last_error", "tw_strerror", "tw_version", "tw_kernel_launch_count",
 ]
 
@@ -77,6 +77,14 @@ class tw_machrep_result(C.Structure):
                 ("up_time_prop", C.c_double), ("immed_prop", C.c_double)]
 
 
+class tw_monitor_state(C.Structure):
+    _fields_ = [("gvt", C.c_double), ("steps", C.c_uint64), ("executed", C.c_uint64), ("rolled_back", C.c_uint64),
+                ("rollbacks", C.c_uint64), ("anti_sent", C.c_uint64), ("annihilated", C.c_uint64),
+                ("sent_local", C.c_uint64), ("sent_remote", C.c_uint64), ("n_lps_local", C.c_uint32), ("rank", C.c_uint32)]
+
+
+MONITOR_FN = C.CFUNCTYPE(None, C.POINTER(tw_monitor_state), C.c_void_p)
+
 _lib = None
 
 
@@ -101,6 +109,7 @@ def load(path=None):
     lib.tw_lp_state_get.argtypes = [H, C.c_uint32, C.POINTER(tw_lp_state)]; lib.tw_lp_state_get.restype = C.c_int
     lib.tw_read_lp_stats.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t]; lib.tw_read_lp_stats.restype = C.c_int
     lib.tw_read_machrep.argtypes = [H, C.c_void_p, C.c_size_t]; lib.tw_read_machrep.restype = C.c_int
+    lib.tw_set_monitor.argtypes = [H, MONITOR_FN, C.c_void_p]; lib.tw_set_monitor.restype = C.c_int
     lib.tw_partition.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; lib.tw_partition.restype = C.c_int
     lib.tw_model_initial_events.argtypes = [C.POINTER(tw_params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.tw_model_initial_events.restype = C.c_int

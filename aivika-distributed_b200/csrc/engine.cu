@@ -252,6 +252,7 @@ struct EngineBase {
     virtual int read_lp_stats(uint64_t *n_exec, uint64_t *hash, size_t n) = 0;
     virtual int read_machrep(tw_machrep_result *out, size_t n) = 0;
     virtual void partition(uint32_t *base, uint32_t *n) const = 0;
+    tw_monitor_fn monitor = nullptr; void *monitor_user = nullptr;
 };
 
 #define TW_CUDA(call)                                                                                   \
@@ -480,6 +481,13 @@ struct Engine : EngineBase {
                 TW_CUDA(cudaEventSynchronize(ev_chk[other]));
                 pending[other] = false;
                 last = h_ctl[other];
+                if (monitor) {
+                    tw_monitor_state ms; memset(&ms, 0, sizeof ms);
+                    ms.gvt = last.gvt; ms.steps = last.c_steps; ms.executed = last.c_exec; ms.rolled_back = last.c_rb_events;
+                    ms.rollbacks = last.c_rollbacks; ms.anti_sent = last.c_anti; ms.annihilated = last.c_annih;
+                    ms.sent_local = last.c_sent_local; ms.sent_remote = last.c_sent_remote; ms.n_lps_local = d.n_local; ms.rank = d.rank;
+                    monitor(&ms, monitor_user);
+                }
                 if ((result = check_device_error(last)) != TW_OK) break;
                 if (!(last.gvt <= until)) { finished = true; break; }
                 if (last.gvt == last_gvt) { if (++stall > 4096) { err = code_name(TW_ERR_DEADLOCK); result = TW_ERR_DEADLOCK; break; } }
@@ -625,6 +633,7 @@ int tw_gvt(tw_engine *e, double *g) { return (e && g) ? e->impl->gvt(g) : TW_ERR
 int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out) { return (e && out) ? e->impl->lp_state(lp, out) : TW_ERR_INVALID_ARG; }
 int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *hash, size_t n) { return (e && n_exec && hash) ? e->impl->read_lp_stats(n_exec, hash, n) : TW_ERR_INVALID_ARG; }
 int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n) { return (e && out) ? e->impl->read_machrep(out, n) : TW_ERR_INVALID_ARG; }
+int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user) { if (!e) return TW_ERR_INVALID_ARG; e->impl->monitor = fn; e->impl->monitor_user = user; return TW_OK; }
 int tw_partition(const tw_engine *e, uint32_t *base, uint32_t *n) { if (!e) return TW_ERR_INVALID_ARG; e->impl->partition(base, n); return TW_OK; }
 
 int tw_model_initial_events(const tw_params *p, tw_event *out, size_t cap, size_t *n)

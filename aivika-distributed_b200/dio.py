@@ -237,6 +237,15 @@ class DIO:
         return LogicalProcessState(s.lp, s.local_time, s.event_queue_time, s.event_queue_size, s.log_size,
                                    s.input_message_count, s.output_message_count, s.rollback_count)
 
+    def setMonitoringAction(self, action):
+        """dioSimulationMonitoringAction (Internal/DIO.hs:453-476): `action(state_dict)` is called every time the
+        engine inspects the device control block during runEventInStopTime (TimeServerState + LP counters)."""
+        def _cb(ptr, _user):
+            st = ptr.contents
+            action({k: getattr(st, k) for k, _ in ffi.tw_monitor_state._fields_})
+        self._monitor_cb = ffi.MONITOR_FN(_cb)           # keep the trampoline alive
+        self._check(self.lib.tw_set_monitor(self.h, self._monitor_cb, None))
+
     # -- results
     def lpStats(self):
         n_exec = np.zeros(self.n_local, dtype=np.uint64); h = np.zeros(self.n_local, dtype=np.uint64)

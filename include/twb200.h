@@ -182,6 +182,21 @@ int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *trace_hash, size_
 /* MachRep2: results of the replicas whose master lives on this partition. */
 int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n_replicas);
 
+/*
+ * Monitoring: dioSimulationMonitoringAction (Internal/DIO.hs:453-476) + TimeServerState
+ * (Optimistic/State.hs:57-68).  The callback runs on the calling thread every time tw_run inspects the device
+ * control block (once per graph launch of steps_per_launch super-steps).
+ */
+typedef struct tw_monitor_state {
+    double   gvt;                 /* tsStateGlobalVirtualTime */
+    uint64_t steps;               /* super-steps since tw_create/tw_reset */
+    uint64_t executed, rolled_back, rollbacks, anti_sent, annihilated, sent_local, sent_remote;
+    uint32_t n_lps_local;         /* tsStateLogicalProcesses (count on this partition) */
+    uint32_t rank;
+} tw_monitor_state;
+typedef void (*tw_monitor_fn)(const tw_monitor_state *state, void *user);
+int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user);
+
 /* Partition geometry: first global LP id and LP count owned by this rank. */
 int tw_partition(const tw_engine *e, uint32_t *lp_base, uint32_t *n_local);
 

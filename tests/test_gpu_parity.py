@@ -203,3 +203,18 @@ def test_cpp_host_mirror_runs_machrep2(H):
     assert r.returncode == 0, r.stderr
     o = H.oracle_machrep(H.machrep_params(1, 1000.0))[0]
     assert f"({o.up_time_prop:.17g},{o.immed_prop:.17g})" in r.stdout
+
+
+def test_monitoring_action(H):
+    """dioSimulationMonitoringAction analogue: periodic engine state with monotone GVT and counters."""
+    d = D()
+    dio = d.DIO(d.PHOLD(4096, remote_pct=30), d.DIOParams(dioTimeHorizon=0.5, stepsPerLaunch=4), d.Specs(0.0, 8.0))
+    seen = []
+    dio.setMonitoringAction(seen.append)
+    dio.enqueueMessages(dio.initialEvents())
+    st = dio.runEventInStopTime()
+    dio.close()
+    assert len(seen) >= 3
+    g = [s["gvt"] for s in seen]; ex = [s["executed"] for s in seen]
+    assert g == sorted(g) and ex == sorted(ex) and seen[0]["n_lps_local"] == 4096
+    assert seen[-1]["executed"] <= st.executed
