@@ -26,6 +26,15 @@ pkg = load_pkg()
 ffi = pkg._ffi
 
 
+def ensure_built():
+    """The CUDA library is a build artefact (git-ignored): compile it when a fresh checkout runs the CPU suite."""
+    if not os.path.exists(ffi.LIB_PATH):
+        subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "csrc"), "libtwb200.so"], check=True, stdout=subprocess.DEVNULL)
+
+
+ensure_built()
+
+
 # ------------------------------------------------------------------ oracle (plain C, test infrastructure)
 class or_event(C.Structure):
     _fields_ = ffi.tw_event._fields_
