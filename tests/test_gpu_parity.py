@@ -218,3 +218,36 @@ def test_monitoring_action(H):
     g = [s["gvt"] for s in seen]; ex = [s["executed"] for s in seen]
     assert g == sorted(g) and ex == sorted(ex) and seen[0]["n_lps_local"] == 4096
     assert seen[-1]["executed"] <= st.executed
+
+
+def test_c2_4096_replicas_match_oracle(H):
+    """BASELINE configs[1]: MachRep2 replicated as 4096 independent groups on one GPU (shortened stop time so the
+    oracle finishes in seconds): every replica's statistics and per-LP traces equal the sequential oracle's, and the
+    population means sit at the documented "about 0.6 and 0.67"."""
+    d = D()
+    n, stop = 4096, 120.0
+    dio, sim = d.runDIO(d.MachRep2(n), d.DIOParams(dioTimeHorizon=2.0, queueCapacity=256, stepsPerLaunch=32),
+                        d.timeServer(3 * n), d.Specs(0.0, stop))
+    st, n_exec, h, res = sim()
+    dio.close()
+    ores = H.oracle_machrep(H.machrep_params(n, stop))
+    o_exec = np.array([r.n_exec[k] for r in ores for k in range(3)], dtype=np.uint64)
+    o_hash = np.array([r.hash[k] for r in ores for k in range(3)], dtype=np.uint64)
+    assert (n_exec == o_exec).all() and (h == o_hash).all()
+    assert (res["up_time_prop"] == np.array([r.up_time_prop for r in ores])).all()
+    assert (res["immed_prop"] == np.array([r.immed_prop for r in ores])).all()
+    assert abs(res["up_time_prop"].mean() - 0.6) < 0.02 and abs(res["immed_prop"].mean() - 0.667) < 0.02
+    assert st.rolled_back > 0
+
+
+def test_random_phold_configurations(H):
+    """Seeded sweep over shapes the fixed cases do not hit (ragged LP counts, tiny populations, every batch size,
+    zero / full remote share, hot sets): the CUDA engine against the oracle, per LP."""
+    rng = np.random.default_rng(20261020)
+    for _ in range(24):
+        n = int(rng.integers(2, 3000)); pop = int(rng.integers(1, 9)); rp = int(rng.choice([0, 5, 50, 100]))
+        hz = float(rng.choice([0.05, 0.1, 0.35, 1.5, -1.0])); batch = int(rng.integers(1, 5))
+        n_hot = int(rng.choice([0, 0, 7])); seed = int(rng.integers(0, 2 ** 31))
+        p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hz, batch=batch, seed=seed,
+                           n_hot=min(n_hot, n), hot_pct=5 if n_hot else 0, cap=1024, steps_per_launch=int(rng.choice([1, 4, 16])))
+        check_phold(H, p)
