@@ -335,6 +335,7 @@ struct Engine : EngineBase {
         d.stop = p.stop_time;
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);
+        d.ablate = (p.flags >> 8) & 7u;      // diagnostic phase ablation for profiles/ (results are meaningless)
         const size_t nl = d.n_local ? d.n_local : 1;
         TW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         TW_CUDA(cudaEventCreate(&ev0)); TW_CUDA(cudaEventCreate(&ev1));
@@ -471,7 +472,9 @@ struct Engine : EngineBase {
         int slot = 0; bool pending[2] = {false, false};
         double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
         Ctl last = c0;
+        uint32_t ablate_launches = 0;
         while (!finished) {
+            if (d.ablate && ablate_launches++ >= 8) break;       // timing-only mode: 8 graph launches, then stop
             TW_CUDA(cudaGraphLaunch(graph, stream)); count(B);
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             TW_CUDA(cudaEventRecord(ev_chk[slot], stream));

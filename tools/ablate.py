@@ -1,0 +1,31 @@
+"""Diagnostic: time k_step with phases switched off (tw_params.flags bits 8..10).  Results of such runs are meaningless;
+only the device time per launch is of interest.  Usage: python tools/ablate.py [c3|c4]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "c4"
+n, rp = ((1 << 20), 50) if wl == "c4" else ((1 << 16), 10)
+lib = H.ffi.load()
+for ab, name in ((0, "full"), (1, "no execute/emit (header + scan + GVT reduction only)")):
+    p = H.phold_params(n, 1000.0, remote_pct=rp, horizon=0.2)
+    p.flags = ab << 8
+    h = C.c_void_p()
+    assert lib.tw_create(C.byref(p), C.byref(h)) == 0
+    cap = n * 16
+    buf = (H.ffi.tw_event * cap)(); cnt = C.c_size_t()
+    lib.tw_model_initial_events(C.byref(p), buf, cap, C.byref(cnt))
+    assert lib.tw_enqueue_messages(h, buf, cnt.value) == 0
+    st = H.ffi.tw_run_stats()
+    if ab == 0:
+        rc = lib.tw_run(h, 1.6, C.byref(st))             # ~20 real super-steps
+        per = st.device_ms * 1e3 / max(1, st.steps)
+    else:
+        rc = lib.tw_run(h, 1000.0, C.byref(st))          # timing-only mode: exactly 8 graph launches x 16 steps
+        per = st.device_ms * 1e3 / 128
+    print(f"{wl} ablate={ab} {name}: {per:.1f} us per launch (rc={rc}, steps={st.steps}, executed={st.executed})", flush=True)
+    lib.tw_destroy(h)
