@@ -90,3 +90,12 @@ def test_machrep2_partitioned_keeps_replicas_whole(H):
 def test_phold_random_configurations(H, n, pop, rp, hor, batch, seed, world, shuffle):
     p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hor, batch=batch, seed=seed, world=world, cap=128)
     check_phold(H, p, seeds=(shuffle,))
+
+
+def test_phold_equal_timestamps_exercise_full_key_ordering(H):
+    """mean 0 makes every delay equal to the lookahead: whole populations share one receive time, so the engine must
+    fall back to the full key (send time, sender, counter) -- including more ties than the candidate list holds."""
+    for n, pop, rp, hz, batch in ((50, 8, 50, 1.0, 4), (200, 6, 30, -1.0, 4), (64, 5, 100, 0.5, 2)):
+        st_ = check_phold(H, H.phold_params(n, 3.0, population=pop, remote_pct=rp, lookahead=0.5, mean=0.0, horizon=hz,
+                                            batch=batch, cap=512), seeds=(3,))
+        assert st_.rolled_back > 0

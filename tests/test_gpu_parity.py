@@ -251,3 +251,11 @@ def test_random_phold_configurations(H):
         p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hz, batch=batch, seed=seed,
                            n_hot=min(n_hot, n), hot_pct=5 if n_hot else 0, cap=1024, steps_per_launch=int(rng.choice([1, 4, 16])))
         check_phold(H, p)
+
+
+def test_phold_equal_timestamps(H):
+    """Degenerate time stamps (mean 0: every event of a generation has the same receive time): tie ordering by the
+    full key and the more-ties-than-candidates path on the device."""
+    for n, pop, rp, hz, batch in ((50, 8, 50, 1.0, 4), (2000, 6, 30, -1.0, 4), (64, 5, 100, 0.5, 2), (5000, 8, 50, 0.5, 3)):
+        check_phold(H, H.phold_params(n, 3.0, population=pop, remote_pct=rp, lookahead=0.5, mean=0.0, horizon=hz,
+                                      batch=batch, cap=512))
