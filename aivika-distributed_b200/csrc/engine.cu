@@ -112,9 +112,9 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
     if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
-    extern __shared__ uint4 tw_stage_smem[];             // per warp: kStage entries x G granules x 32 lanes x 16 B
+    extern __shared__ uint4 tw_stage_smem[];             // per warp: kStageSlots records x G granules x 32 lanes x 16 B
     Stage<M> stg;
-    stg.base = tw_stage_smem + (threadIdx.x >> 5) * (M::kStage * Stage<M>::G * 32) + (threadIdx.x & 31);
+    stg.base = tw_stage_smem + (threadIdx.x >> 5) * (kStageSlots * Stage<M>::G * 32) + (threadIdx.x & 31);
     lp_step<M>(d, acc, stg, l, gvt, wend, step & 1u);  // all lanes enter: phases reconverge inside
     if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
     block_finish(ctl, acc, step, d.world, true);
@@ -335,7 +335,7 @@ struct Engine : EngineBase {
         d.stop = p.stop_time;
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);
-        d.ablate = (p.flags >> 8) & 7u;      // diagnostic phase ablation for profiles/ (results are meaningless)
+        d.ablate = (p.flags >> 8) & 63u;      // diagnostic phase ablation for profiles/ (results are meaningless)
         const size_t nl = d.n_local ? d.n_local : 1;
         TW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         TW_CUDA(cudaEventCreate(&ev0)); TW_CUDA(cudaEventCreate(&ev1));
@@ -357,7 +357,7 @@ struct Engine : EngineBase {
     }
 
     // exchange cudaIpc handles of pages / inbox counters through NCCL and map every peer (NVLink P2P)
-    static size_t stage_bytes() { return (size_t)(kBlock / 32) * M::kStage * Stage<M>::G * 32 * sizeof(uint4); }
+    static size_t stage_bytes() { return (size_t)(kBlock / 32) * kStageSlots * Stage<M>::G * 32 * sizeof(uint4); }
 
     int init_peers()
     {

@@ -23,18 +23,8 @@ constexpr uint64_t kCtrMask = ~(kAntiBit | kDeadBit | kNoopBit);
 enum HandlerStatus { H_OK = 0, H_RETRY = 1, H_BAD = 2 };
 
 // ------------------------------------------------------------------ PHOLD
-// Ring entries staged in shared memory per LP and step (0 = read the ring directly from global memory).
-// Staging was measured slower on B200 (profiles/r1_tuning.md): it caps residency at 6-8 warps/SM while the step is
-// bound by issue latency, not by dependent round trips.  Kept as a compile-time mode for the next round.
-#ifndef TW_STAGE_PHOLD
-#define TW_STAGE_PHOLD 0
-#endif
-#ifndef TW_STAGE_MACHREP
-#define TW_STAGE_MACHREP 0
-#endif
 struct PholdModel {
     static constexpr int kMaxSends = 1;
-    static constexpr int kStage = TW_STAGE_PHOLD;      // ring entries staged in shared memory per LP and step
     struct alignas(32) Event {             // 32 B: one DRAM sector
         double   recv_ts, send_ts;
         uint64_t ctr;
@@ -118,7 +108,6 @@ struct PholdModel {
 // (tests/MachRep2DistributedReproducible.hs:125-229).
 struct MachRepModel {
     static constexpr int kMaxSends = 3;
-    static constexpr int kStage = TW_STAGE_MACHREP;
     struct alignas(16) Event {             // 48 B
         double   recv_ts, send_ts;
         uint64_t ctr;
