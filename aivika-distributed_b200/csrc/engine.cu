@@ -307,6 +307,7 @@ struct Engine : EngineBase {
     std::vector<void *> peer_ptrs;        // opened IPC mappings
     uint64_t launches = 0;
     int grid = 0;
+    void *meta = nullptr; size_t meta_bytes = 0, l2_window_bytes = 0, l2_persist_bytes = 0;
 
     int init(const tw_params &p)
     {
@@ -343,14 +344,41 @@ struct Engine : EngineBase {
         TW_CUDA(cudaEventCreateWithFlags(&ev_chk[1], cudaEventDisableTiming));
         TW_CUDA(cudaMalloc(&d.pages, nl * cap * sizeof(typename M::Event)));
         TW_CUDA(cudaMalloc(&d.saved, nl * cap * sizeof(typename M::State)));
-        TW_CUDA(cudaMalloc(&d.state, nl * sizeof(typename M::State)));
-        TW_CUDA(cudaMalloc(&d.hdr, nl * sizeof(LPHdr)));
-        TW_CUDA(cudaMalloc(&d.in, nl * sizeof(LPIn)));
+        // per-LP metadata in ONE allocation, hottest first: inbox counters | headers | model state.  An L2 persisting
+        // window is laid over it below (the slot-reservation atomics and header reads then hit L2).
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t off_hdr = up(nl * sizeof(LPIn)), off_state = off_hdr + up(nl * sizeof(LPHdr));
+        meta_bytes = off_state + up(nl * sizeof(typename M::State));
+        TW_CUDA(cudaMalloc(&meta, meta_bytes));
+        d.in = (LPIn *)meta; d.hdr = (LPHdr *)((char *)meta + off_hdr); d.state = (typename M::State *)((char *)meta + off_state);
         TW_CUDA(cudaMalloc(&d.ctl, sizeof(Ctl)));
         TW_CUDA(cudaMalloc(&d_tmp, 2 * sizeof(unsigned long long)));
         TW_CUDA(cudaHostAlloc(&h_ctl, 2 * sizeof(Ctl), cudaHostAllocDefault));
         grid = (int)((nl + kBlock - 1) / kBlock);
         TW_CUDA(cudaFuncSetAttribute(k_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
+        // Keep the per-LP metadata resident in L2 with a persisting access-policy window (kernel nodes captured from
+        // this stream inherit it).  TWB200_L2_WINDOW_MB overrides the size (0 = off); default = the inbox counters.
+        {
+            size_t want = nl * sizeof(LPIn);               // measured best: pin the inbox counters only (profiles/r1_tuning.md)
+            if (const char *e = getenv("TWB200_L2_WINDOW_MB")) want = (size_t)atol(e) << 20;
+            int max_win = 0, max_persist = 0;
+            cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            if (want > meta_bytes) want = meta_bytes;
+            if (want > (size_t)max_win) want = (size_t)max_win;
+            if (want > 0 && max_persist > 0) {
+                const size_t persist = want < (size_t)max_persist ? want : (size_t)max_persist;
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
+                cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+                av.accessPolicyWindow.base_ptr = meta; av.accessPolicyWindow.num_bytes = want;
+                av.accessPolicyWindow.hitRatio = (float)((double)persist / (double)want);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                cudaGetLastError();
+                l2_window_bytes = want; l2_persist_bytes = persist;
+            }
+        }
         d.peer_pages[d.rank] = d.pages; d.peer_in[d.rank] = d.in;
         if (p.world > 1) { int rc = init_peers(); if (rc) return rc; }
         return reset();
@@ -576,7 +604,7 @@ struct Engine : EngineBase {
         if (graph) cudaGraphExecDestroy(graph);
         for (void *p : peer_ptrs) cudaIpcCloseMemHandle(p);
         if (comm) g_nccl.CommDestroy(comm);
-        cudaFree(d.pages); cudaFree(d.saved); cudaFree(d.state); cudaFree(d.hdr); cudaFree(d.in); cudaFree(d.ctl);
+        cudaFree(d.pages); cudaFree(d.saved); cudaFree(meta); cudaFree(d.ctl);
         cudaFree(d_stage); cudaFree(d_tmp);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
