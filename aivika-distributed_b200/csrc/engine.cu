@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_ti
     if (l >= d.n_local) return;
     LPHdr h; h.head = 0; h.nproc = 0; h.consumed = 0; h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
     d.hdr[l] = h;
-    LPIn in; in.total = 0; in.cnt[0] = 0; in.cnt[1] = 0; in.pad = 0;
+    LPIn in; in.word = 0;
     d.in[l] = in;
     d.state[l] = M::initial_state(d.mp, d.lp_base + l);
 }
@@ -573,8 +573,8 @@ struct Engine : EngineBase {
         TW_CUDA(cudaStreamSynchronize(stream));
         memset(out, 0, sizeof *out);
         out->lp = lp; out->local_time = h.lvt; out->event_queue_time = h.min_pend;
-        out->event_queue_size = in.total - h.head - h.nproc;
-        out->log_size = h.nproc; out->input_message_count = in.total - h.head; out->output_message_count = h.nproc;
+        out->event_queue_size = in_total(in.word) - h.head - h.nproc;
+        out->log_size = h.nproc; out->input_message_count = in_total(in.word) - h.head; out->output_message_count = h.nproc;
         out->rollback_count = h_ctl[0].c_rollbacks; out->executed = s.n_exec; out->trace_hash = s.hash;
         return TW_OK;
     }

@@ -51,7 +51,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         d.pages = P.pages.data(); d.saved = P.saved.data(); d.state = P.state.data(); d.hdr = P.hdr.data(); d.in = P.in.data();
         for (uint32_t l = 0; l < d.n_local; ++l) {
             LPHdr h; h.head = h.nproc = h.consumed = h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
-            P.hdr[l] = h; LPIn in; in.total = in.cnt[0] = in.cnt[1] = in.pad = 0; P.in[l] = in;
+            P.hdr[l] = h; LPIn in; in.word = 0; P.in[l] = in;
             P.state[l] = M::initial_state(d.mp, d.lp_base + l);
         }
     }
@@ -94,7 +94,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     // reported through the otherwise unused kernel_launches field so tests can close the balance anti_sent == annihilated + left
     for (uint32_t r = 0; r < W; ++r)
         for (uint32_t l = 0; l < parts[r].d.n_local; ++l)
-            for (uint32_t a = parts[r].hdr[l].consumed; a != parts[r].in[l].total; ++a)
+            for (uint32_t a = parts[r].hdr[l].consumed; a != in_total(parts[r].in[l].word); ++a)
                 if (parts[r].pages[(size_t)l * cap + (a & (cap - 1))].ctr & kAntiBit) S.kernel_launches++;
     for (uint32_t r = 0; r < W; ++r)
         for (uint32_t l = 0; l < parts[r].d.n_local; ++l) {
