@@ -9,8 +9,8 @@
 //   k_init<M>     newEventQueue for every LP (Internal/Event.hs:92-116)
 //   k_collect<M>  committed-event count and trace-hash sum
 // Multi-GPU: LP ranges are sharded (LP i lives on rank i / n_per); remote sends are direct NVLink peer
-// stores + peer atomics issued from inside k_step (no staging, no separate exchange kernel), and GVT is an
-// ncclAllReduce(min) of one double between steps.
+// stores + peer atomics issued from inside k_step (no staging, no separate exchange kernel), and GVT is a
+// peer-memory mailbox exchange (k_gvt_exchange); NCCL is used for set-up and the collective host-side barriers only.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -144,6 +144,51 @@ __global__ void __launch_bounds__(kBlock) k_route(const Dev<M> d, const tw_event
     }
 }
 
+// Cross-GPU GVT: every rank publishes its local minimum for step `tag` into the mailbox of every peer (NVLink peer
+// stores) and waits until all `world` entries for that step have arrived, then takes the minimum -- the
+// LocalTimeMessage / GlobalTimeMessage round of the Time Server (Internal/TimeServer.hs:253-270, 384-421) without a
+// server and without NCCL on the per-step path (an 8-byte ncclAllReduce costs ~20-40 us, this ~5 us).  It is also the
+// barrier that orders the peer stores of super-step s before the loads of super-step s+1.  One warp; waits are
+// bounded so that a lost peer becomes an error code, never a hang.  One rank per GPU is required (and enforced).
+__global__ void k_gvt_exchange(Ctl *ctl, GvtSlot *const *peer_slots_dev, uint32_t rank, uint32_t world)
+{
+    const uint32_t r = threadIdx.x;
+    const uint32_t tag = *(volatile uint32_t *)&ctl->step;
+    const uint32_t par = tag & 1u;
+    const bool aborted = *(volatile uint32_t *)&ctl->error != 0;
+    if (r < world) {
+        GvtSlot *dst = peer_slots_dev[r] + par * kMaxWorld + rank;       // my entry in rank r's mailbox
+        if (aborted) {
+            *(volatile uint32_t *)&(peer_slots_dev[r] + 0 * kMaxWorld + rank)->tag = kSlotAbort;
+            *(volatile uint32_t *)&(peer_slots_dev[r] + 1 * kMaxWorld + rank)->tag = kSlotAbort;
+        } else {
+            *(volatile double *)&dst->value = *(volatile double *)&ctl->gvt_local;
+            __threadfence_system();
+            *(volatile uint32_t *)&dst->tag = tag;
+        }
+    }
+    if (aborted) return;
+    double v = pos_inf(); uint32_t bad = 0;
+    if (r < world) {
+        const GvtSlot *src = peer_slots_dev[rank] + par * kMaxWorld + r;  // rank r's entry in my mailbox
+        uint32_t t = *(volatile const uint32_t *)&src->tag, spins = 0;
+        while (t != tag) {
+            if (t == kSlotAbort) { bad = TW_ERR_CUDA; break; }
+            if (++spins > 4000000u) { bad = TW_ERR_DEADLOCK; break; }     // seconds: a peer is gone
+            __nanosleep(64);
+            t = *(volatile const uint32_t *)&src->tag;
+        }
+        __threadfence_system();
+        v = *(volatile const double *)&src->value;
+    }
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    const unsigned long long m = warp_min_u64(ordered_bits(v));
+    if (r == 0) {
+        if (bad) { if (atomicCAS(&ctl->error, 0u, bad) == 0u) ctl->err_lp = 0xFFFFFFFFu; }
+        else ctl->gvt = from_ordered(m);
+    }
+}
+
 // after k_route: gvt = min(gvt, injected minimum)   (single thread)
 __global__ void k_fold_inject(Ctl *ctl)
 {
@@ -158,7 +203,10 @@ __global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_ti
 {
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
     if (l == 0) {
+        // the step counter is never rewound: it tags the cross-GPU GVT mailboxes, and a tag must not repeat across runs
+        const uint32_t next_step = d.ctl->step + 2u;
         Ctl c; memset(&c, 0, sizeof c);
+        c.step = next_step;
         c.gvt = start_time; c.gvt_local = start_time;
         c.pend_min = ordered_bits(pos_inf()); c.emit_min = ordered_bits(pos_inf());
         *d.ctl = c;
@@ -308,6 +356,7 @@ struct Engine : EngineBase {
     uint64_t launches = 0;
     int grid = 0;
     void *meta = nullptr; size_t meta_bytes = 0, l2_window_bytes = 0, l2_persist_bytes = 0;
+    GvtSlot *d_slots = nullptr; GvtSlot **d_peer_slots = nullptr;      // my GVT mailbox; device copy of the peer table
 
     int init(const tw_params &p)
     {
@@ -352,6 +401,7 @@ struct Engine : EngineBase {
         TW_CUDA(cudaMalloc(&meta, meta_bytes));
         d.in = (LPIn *)meta; d.hdr = (LPHdr *)((char *)meta + off_hdr); d.state = (typename M::State *)((char *)meta + off_state);
         TW_CUDA(cudaMalloc(&d.ctl, sizeof(Ctl)));
+        TW_CUDA(cudaMemset(d.ctl, 0, sizeof(Ctl)));
         TW_CUDA(cudaMalloc(&d_tmp, 2 * sizeof(unsigned long long)));
         TW_CUDA(cudaHostAlloc(&h_ctl, 2 * sizeof(Ctl), cudaHostAllocDefault));
         grid = (int)((nl + kBlock - 1) / kBlock);
@@ -392,10 +442,14 @@ struct Engine : EngineBase {
         if (!g_nccl.load(err)) return TW_ERR_CUDA;
         NcclApi::Id128 id; memcpy(id.b, P.nccl_id, 128);
         TW_NCCL(g_nccl.CommInitRank(&comm, (int)P.world, id, (int)P.rank));
-        struct Handles { cudaIpcMemHandle_t pages, in; };
+        struct Handles { cudaIpcMemHandle_t pages, in, slots; };
         Handles mine; Handles *d_all = nullptr;
         TW_CUDA(cudaIpcGetMemHandle(&mine.pages, d.pages));
         TW_CUDA(cudaIpcGetMemHandle(&mine.in, d.in));
+        TW_CUDA(cudaMalloc(&d_slots, 2 * kMaxWorld * sizeof(GvtSlot)));
+        TW_CUDA(cudaMemset(d_slots, 0xFE, 2 * kMaxWorld * sizeof(GvtSlot)));
+        TW_CUDA(cudaIpcGetMemHandle(&mine.slots, d_slots));
+        d.peer_slots[d.rank] = d_slots;
         TW_CUDA(cudaMalloc(&d_all, sizeof(Handles) * P.world));
         TW_CUDA(cudaMemcpyAsync(d_all + P.rank, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
         TW_NCCL(g_nccl.AllGather(d_all + P.rank, d_all, sizeof(Handles), kNcclInt8, comm, stream));
@@ -405,11 +459,28 @@ struct Engine : EngineBase {
         TW_CUDA(cudaFree(d_all));
         for (uint32_t r = 0; r < P.world; ++r) {
             if (r == P.rank) continue;
-            void *pp = nullptr, *pi = nullptr;
+            void *pp = nullptr, *pi = nullptr, *ps = nullptr;
             TW_CUDA(cudaIpcOpenMemHandle(&pp, all[r].pages, cudaIpcMemLazyEnablePeerAccess));
             TW_CUDA(cudaIpcOpenMemHandle(&pi, all[r].in, cudaIpcMemLazyEnablePeerAccess));
-            peer_ptrs.push_back(pp); peer_ptrs.push_back(pi);
-            d.peer_pages[r] = (typename M::Event *)pp; d.peer_in[r] = (LPIn *)pi;
+            TW_CUDA(cudaIpcOpenMemHandle(&ps, all[r].slots, cudaIpcMemLazyEnablePeerAccess));
+            peer_ptrs.push_back(pp); peer_ptrs.push_back(pi); peer_ptrs.push_back(ps);
+            d.peer_pages[r] = (typename M::Event *)pp; d.peer_in[r] = (LPIn *)pi; d.peer_slots[r] = (GvtSlot *)ps;
+        }
+        TW_CUDA(cudaMalloc(&d_peer_slots, kMaxWorld * sizeof(GvtSlot *)));
+        TW_CUDA(cudaMemcpy(d_peer_slots, d.peer_slots, kMaxWorld * sizeof(GvtSlot *), cudaMemcpyHostToDevice));
+        // one rank per GPU: the mailbox exchange spins on peers, two ranks sharing a GPU could starve each other
+        {
+            int dev = 0; cudaGetDevice(&dev);
+            char mine_id[64] = {0}; cudaDeviceGetPCIBusId(mine_id, sizeof mine_id, dev);
+            char *d_ids = nullptr; std::vector<char> ids(64 * P.world);
+            TW_CUDA(cudaMalloc(&d_ids, 64 * P.world));
+            TW_CUDA(cudaMemcpyAsync(d_ids + 64 * P.rank, mine_id, 64, cudaMemcpyHostToDevice, stream));
+            TW_NCCL(g_nccl.AllGather(d_ids + 64 * P.rank, d_ids, 64, kNcclInt8, comm, stream));
+            TW_CUDA(cudaMemcpyAsync(ids.data(), d_ids, 64 * P.world, cudaMemcpyDeviceToHost, stream));
+            TW_CUDA(cudaStreamSynchronize(stream));
+            TW_CUDA(cudaFree(d_ids));
+            for (uint32_t r = 0; r < P.world; ++r)
+                if (r != P.rank && !strncmp(ids.data() + 64 * r, mine_id, 64)) { err = "two ranks share one GPU: multi-rank runs need one GPU per rank"; return TW_ERR_INVALID_ARG; }
         }
         return TW_OK;
     }
@@ -426,6 +497,7 @@ struct Engine : EngineBase {
     {
         k_init<M><<<grid, kBlock, 0, stream>>>(d, P.start_time); count(1);
         TW_CUDA(cudaGetLastError());
+        if (d_slots) TW_CUDA(cudaMemsetAsync(d_slots, 0xFE, 2 * kMaxWorld * sizeof(GvtSlot), stream));   // tags = kSlotEmpty
         TW_CUDA(cudaStreamSynchronize(stream));
         if (P.world > 1) { int rc = barrier_all(); if (rc) return rc; TW_CUDA(cudaStreamSynchronize(stream)); }
         return TW_OK;
@@ -472,8 +544,12 @@ struct Engine : EngineBase {
         for (uint32_t i = 0; i < steps; ++i) {
             k_step<M><<<grid, kBlock, stage_bytes(), stream>>>(d);
             if (P.world > 1) {
-                int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);
-                if (e) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); err = "ncclAllReduce failed during capture"; return TW_ERR_CUDA; }
+                if (getenv("TWB200_NCCL_GVT")) {         // fallback / comparison: ncclAllReduce(min) per super-step
+                    int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);
+                    if (e) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); err = "ncclAllReduce failed during capture"; return TW_ERR_CUDA; }
+                } else {
+                    k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.rank, d.world);
+                }
             }
         }
         TW_CUDA(cudaStreamEndCapture(stream, &g));
@@ -503,7 +579,7 @@ struct Engine : EngineBase {
         uint32_t ablate_launches = 0;
         while (!finished) {
             if (d.ablate && ablate_launches++ >= 8) break;       // timing-only mode: 8 graph launches, then stop
-            TW_CUDA(cudaGraphLaunch(graph, stream)); count(B);
+            TW_CUDA(cudaGraphLaunch(graph, stream)); count(P.world > 1 ? 2 * B : B);
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             TW_CUDA(cudaEventRecord(ev_chk[slot], stream));
             pending[slot] = true;
@@ -605,7 +681,7 @@ struct Engine : EngineBase {
         for (void *p : peer_ptrs) cudaIpcCloseMemHandle(p);
         if (comm) g_nccl.CommDestroy(comm);
         cudaFree(d.pages); cudaFree(d.saved); cudaFree(meta); cudaFree(d.ctl);
-        cudaFree(d_stage); cudaFree(d_tmp);
+        cudaFree(d_stage); cudaFree(d_tmp); cudaFree(d_slots); cudaFree(d_peer_slots);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
         if (ev_chk[0]) cudaEventDestroy(ev_chk[0]); if (ev_chk[1]) cudaEventDestroy(ev_chk[1]);
