@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
     if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
-    extern __shared__ uint4 tw_stage_smem[];             // per warp: kStageSlots records x G granules x 32 lanes x 16 B
-    Stage<M> stg;
-    stg.base = tw_stage_smem + (threadIdx.x >> 5) * (kStageSlots * Stage<M>::G * 32) + (threadIdx.x & 31);
-    lp_step<M>(d, acc, stg, l, gvt, wend, step & 1u);  // all lanes enter: phases reconverge inside
+    extern __shared__ uint4 tw_queue_smem[];             // per warp: kQueueSlots work items (tw_core.cuh, WorkQ)
+    WorkQ<M> q;
+    q.init(reinterpret_cast<typename M::Work *>(tw_queue_smem) + (threadIdx.x >> 5) * kQueueSlots);
+    lp_step<M>(d, acc, q, l, gvt, wend, step & 1u);    // all lanes enter: phases reconverge inside
     if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
     block_finish(ctl, acc, step, d.world, true);
 }
@@ -365,7 +365,7 @@ struct Engine : EngineBase {
         uint32_t cap = p.queue_capacity ? p.queue_capacity : 128;
         if (cap & (cap - 1)) { err = "queue_capacity must be a power of two"; return TW_ERR_INVALID_ARG; }
         if (cap < 8) { err = "queue_capacity must be >= 8"; return TW_ERR_INVALID_ARG; }
-        uint32_t mb = p.max_events_per_step ? p.max_events_per_step : kMaxBatch;
+        uint32_t mb = p.max_events_per_step ? p.max_events_per_step : 8;
         if (mb > (uint32_t)kMaxBatch) mb = kMaxBatch;
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { err = "no CUDA device: the engine has no CPU fallback"; return TW_ERR_CUDA; }
@@ -385,7 +385,6 @@ struct Engine : EngineBase {
         d.stop = p.stop_time;
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);
-        d.ablate = (p.flags >> 8) & 63u;      // diagnostic phase ablation for profiles/ (results are meaningless)
         const size_t nl = d.n_local ? d.n_local : 1;
         TW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         TW_CUDA(cudaEventCreate(&ev0)); TW_CUDA(cudaEventCreate(&ev1));
@@ -435,7 +434,7 @@ struct Engine : EngineBase {
     }
 
     // exchange cudaIpc handles of pages / inbox counters through NCCL and map every peer (NVLink P2P)
-    static size_t stage_bytes() { return (size_t)(kBlock / 32) * kStageSlots * Stage<M>::G * 32 * sizeof(uint4); }
+    static size_t stage_bytes() { return (size_t)(kBlock / 32) * kQueueSlots * sizeof(typename M::Work); }   // work queues
 
     int init_peers()
     {
@@ -576,9 +575,7 @@ struct Engine : EngineBase {
         int slot = 0; bool pending[2] = {false, false};
         double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
         Ctl last = c0;
-        uint32_t ablate_launches = 0;
         while (!finished) {
-            if (d.ablate && ablate_launches++ >= 8) break;       // timing-only mode: 8 graph launches, then stop
             TW_CUDA(cudaGraphLaunch(graph, stream)); count(P.world > 1 ? 2 * B : B);
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             TW_CUDA(cudaEventRecord(ev_chk[slot], stream));

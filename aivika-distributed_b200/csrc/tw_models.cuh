@@ -6,6 +6,15 @@
 // Purity is what lets the engine regenerate anti-messages by replaying the handler on the saved
 // pre-state instead of keeping an OutputMessageQueue (Internal/OutputMessageQueue.hs:81-104).
 //
+// The engine runs a handler in two parts so that the expensive one can be spread over all lanes of a warp
+// (tw_core.cuh, WorkQ):
+//   advance(params, lp, state, event) -> status   the sequential state transition of the LP (cheap, one LP = one lane)
+//   Work                                           what is needed to produce the messages of that execution
+//   emit(params, work, out[], n_out)               the messages themselves; pure, runs on whichever lane is free
+// A model with kSplit = true derives Work from (pre-state, event) and does the heavy arithmetic in emit (PHOLD:
+// the draws, the logarithm and the destination); a model with kSplit = false computes its messages inside
+// handle() and a Work item is simply one finished message.
+//
 // Event.ctr: bits 0..60 = per-sender send counter (part of the saved state, so it is rollback
 // invariant, unlike generateMessageSequenceNo, Internal/OutputMessageQueue.hs:119-122),
 // bit 63 = anti-message toggle (Internal/Message.hs:48), bit 62 = annihilated, bit 61 = processed as no-op.
@@ -59,18 +68,37 @@ struct PholdModel {
         return e;
     }
     // One event execution: draw the delay and the destination, send one message.
-    TW_HD static int handle(const Params &p, uint32_t lp, State &s, const Event &e, Event *out, int &n_out)
+    static constexpr bool kSplit = true;
+    struct alignas(16) Work {              // 32 B: the part of (pre-state, event) the sent message depends on
+        double   now;
+        uint64_t rng_ctr, send_ctr;
+        uint32_t lp, anti;
+    };
+    TW_HD static Work make_work(uint32_t lp, const State &pre, const Event &e, bool anti)
     {
+        Work w; w.now = e.recv_ts; w.rng_ctr = pre.rng_ctr; w.send_ctr = pre.send_ctr; w.lp = lp; w.anti = anti ? 1u : 0u;
+        return w;
+    }
+    TW_HD static uint32_t work_lp(const Work &w) { return w.lp; }
+    TW_HD static int advance(const Params &, uint32_t, State &s, const Event &e)
+    {
+        s.hash = trace_fold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
+        s.rng_ctr += 4; s.send_ctr += 1; s.n_exec += 1;
+        return H_OK;
+    }
+    TW_HD static void emit(const Params &p, const Work &w, Event *out, int &n_out)
+    {
+        const uint32_t lp = w.lp;
         const uint64_t key = lp_stream_key(p.seed, lp);
-        const uint64_t d1 = stream_draw(key, s.rng_ctr);
-        const uint64_t d2 = stream_draw(key, s.rng_ctr + 1);
-        const double now = e.recv_ts;
+        const uint64_t d1 = stream_draw(key, w.rng_ctr);
+        const uint64_t d2 = stream_draw(key, w.rng_ctr + 1);
+        const double now = w.now;
         const double delay = fadd(p.lookahead, expo_variate(uniform01(d1), p.mean));
         uint32_t dst = lp;
         const uint64_t N = p.n_lps;
         if (N > 1 && (((d2 >> 32) * 100ull) >> 32) < p.remote_pct) {
-            const uint64_t d3 = stream_draw(key, s.rng_ctr + 2);
-            const uint64_t d4 = stream_draw(key, s.rng_ctr + 3);
+            const uint64_t d3 = stream_draw(key, w.rng_ctr + 2);
+            const uint64_t d4 = stream_draw(key, w.rng_ctr + 3);
             if (p.n_hot > 0 && (((d4 >> 32) * 100ull) >> 32) < p.hot_pct) {
                 const uint64_t k = mulhi64(d3, p.n_hot);
                 dst = (uint32_t)((k * N) / p.n_hot);
@@ -80,11 +108,14 @@ struct PholdModel {
             }
         }
         Event &o = out[0];
-        o.recv_ts = fadd(now, delay); o.send_ts = now; o.ctr = s.send_ctr; o.src = lp; o.dst = dst;
+        o.recv_ts = fadd(now, delay); o.send_ts = now; o.ctr = w.send_ctr | (w.anti ? kAntiBit : 0ull); o.src = lp; o.dst = dst;
         n_out = 1;
-        s.hash = trace_fold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
-        s.rng_ctr += 4; s.send_ctr += 1; s.n_exec += 1;
-        return H_OK;
+    }
+    // the undivided handler (advance after emit): what one execution does as a whole
+    TW_HD static int handle(const Params &p, uint32_t lp, State &s, const Event &e, Event *out, int &n_out)
+    {
+        emit(p, make_work(lp, s, e, false), out, n_out);
+        return advance(p, lp, s, e);
     }
     static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
@@ -108,6 +139,7 @@ struct PholdModel {
 // (tests/MachRep2DistributedReproducible.hs:125-229).
 struct MachRepModel {
     static constexpr int kMaxSends = 3;
+    static constexpr bool kSplit = false;      // messages are computed inside handle(); a Work item is one finished message
     struct alignas(16) Event {             // 48 B
         double   recv_ts, send_ts;
         uint64_t ctr;
@@ -115,6 +147,7 @@ struct MachRepModel {
         uint32_t type, pad;
         double   value;
     };
+    using Work = Event;
     struct alignas(16) State {             // 64 B; master and slave views share the record
         double   total_up_time;            // master :167
         int64_t  n_rep, n_immed;           // master :168-169
@@ -155,6 +188,8 @@ struct MachRepModel {
         e.type = w.type; e.pad = 0; e.value = w.value;
         return e;
     }
+    TW_HD static uint32_t work_lp(const Event &w) { return w.src; }
+    TW_HD static void emit(const Params &, const Event &w, Event *out, int &n_out) { out[0] = w; n_out = 1; }
     TW_HD static void send(State &s, uint32_t from, uint32_t to, double now, double at, uint32_t type, double value,
                            Event *out, int &n_out)
     {

@@ -41,7 +41,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         d.n_global = p->n_lps; d.world = W; d.rank = r; d.n_per = n_per; d.lp_base = n_per * r;
         d.n_local = d.lp_base >= p->n_lps ? 0 : std::min(n_per, p->n_lps - d.lp_base);
         d.cap = cap; d.mask = cap - 1;
-        d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : kMaxBatch;
+        d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : 8;
         d.proc_limit = p->proc_limit ? p->proc_limit : cap / 4;
         d.fossil_thresh = p->fossil_threshold ? p->fossil_threshold : cap / 8;
         d.stop = p->stop_time; d.horizon = (p->time_horizon >= 0.0) ? p->time_horizon : -1.0;
@@ -80,7 +80,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
         if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
         acc.init();
-        for (auto &o : order) { Stage<M> stg; lp_step<M>(parts[o.first].d, acc, stg, o.second, gvt, wend, step & 1u); }
+        for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step & 1u); }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
         const double g = std::min(acc.pend_min, acc.emit_min);
         if (g < gvt) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", gvt, g, step); return 100; }

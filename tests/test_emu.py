@@ -21,9 +21,9 @@ def check_phold(H, p, seeds=(0, 1)):
 
 
 @pytest.mark.parametrize("horizon", [0.1, 0.5, 2.0, -1.0])
-@pytest.mark.parametrize("batch", [1, 4])
+@pytest.mark.parametrize("batch", [1, 4, 16, 64])
 def test_phold_all_horizons_commit_the_sequential_schedule(H, horizon, batch):
-    st_ = check_phold(H, H.phold_params(300, 6.0, remote_pct=40, horizon=horizon, batch=batch))
+    st_ = check_phold(H, H.phold_params(300, 6.0, remote_pct=40, horizon=horizon, batch=batch, cap=128 if batch <= 4 else 512))
     if horizon == 0.1:
         assert st_.rolled_back == 0 and st_.anti_sent == 0      # window == lookahead is conservative
     if horizon != 0.1:
@@ -43,6 +43,17 @@ def test_phold_skewed_fanout_and_small_ring(H):
     assert st_.rolled_back > 0
     # tiny ring: optimism stalls on proc_limit and tombstones are compacted, results must not change
     check_phold(H, H.phold_params(64, 6.0, remote_pct=50, population=4, horizon=-1.0, cap=64, proc_limit=4, fossil=2))
+
+
+@pytest.mark.parametrize("batch", [2, 8, 64])
+def test_phold_long_pending_regions_take_the_whole_region_search(H, batch):
+    """A few very hot LPs collect far more than 64 pending events: their selection cannot use the 64-bit window mask and
+    goes through the search over the whole region (cooperative on the GPU), including equal-time ties."""
+    st_ = check_phold(H, H.phold_params(128, 3.0, population=8, remote_pct=80, n_hot=2, hot_pct=60, horizon=1.0, cap=2048,
+                                        batch=batch, proc_limit=512))
+    assert st_.rolled_back > 0
+    check_phold(H, H.phold_params(96, 4.0, population=8, remote_pct=90, n_hot=1, hot_pct=100, lookahead=0.5, mean=0.0,
+                                  horizon=-1.0, cap=2048, batch=batch, proc_limit=512), seeds=(2,))
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
@@ -86,9 +97,9 @@ def test_machrep2_partitioned_keeps_replicas_whole(H):
 
 @settings(max_examples=25, deadline=None)
 @given(n=st.integers(2, 200), pop=st.integers(1, 6), rp=st.integers(0, 100), hor=st.sampled_from([0.05, 0.3, 1.5, -1.0]),
-       batch=st.integers(1, 4), seed=st.integers(0, 2 ** 32), world=st.sampled_from([1, 2, 4]), shuffle=st.integers(0, 99))
+       batch=st.sampled_from([1, 2, 3, 4, 7, 16, 64]), seed=st.integers(0, 2 ** 32), world=st.sampled_from([1, 2, 4]), shuffle=st.integers(0, 99))
 def test_phold_random_configurations(H, n, pop, rp, hor, batch, seed, world, shuffle):
-    p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hor, batch=batch, seed=seed, world=world, cap=128)
+    p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hor, batch=batch, seed=seed, world=world, cap=128 if batch <= 4 else 512)
     check_phold(H, p, seeds=(shuffle,))
 
 
