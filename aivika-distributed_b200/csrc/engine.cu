@@ -28,10 +28,10 @@ namespace twb {
 
 // Launch shape of k_step, chosen by the sweep in profiles/r1_tuning.md (tools/sweep_variants.sh)
 #ifndef TW_BLOCK
-#define TW_BLOCK 256
+#define TW_BLOCK 128
 #endif
 #ifndef TW_MINBLOCKS
-#define TW_MINBLOCKS 2
+#define TW_MINBLOCKS 4
 #endif
 constexpr int kBlock = TW_BLOCK;
 static std::atomic<uint64_t> g_launches{0};
@@ -111,11 +111,14 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
     double wend = d.stop;
     if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
-    const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
     extern __shared__ uint4 tw_queue_smem[];             // per warp: kQueueSlots work items (tw_core.cuh, WorkQ)
     WorkQ<M> q;
     q.init(reinterpret_cast<typename M::Work *>(tw_queue_smem) + (threadIdx.x >> 5) * kQueueSlots);
-    lp_step<M>(d, acc, q, l, gvt, wend, step & 1u);    // all lanes enter: phases reconverge inside
+    // one warp = d.tiles consecutive tiles of 32 LPs; the work queue is carried from tile to tile
+    const uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
+    for (uint32_t t = 0; t < d.tiles; ++t)
+        lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+    q.drain(d, acc, step & 1u);
     if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
     block_finish(ctl, acc, step, d.world, true);
 }
@@ -354,7 +357,7 @@ struct Engine : EngineBase {
     void *comm = nullptr;                 // ncclComm_t
     std::vector<void *> peer_ptrs;        // opened IPC mappings
     uint64_t launches = 0;
-    int grid = 0;
+    int grid = 0, step_grid = 0;
     void *meta = nullptr; size_t meta_bytes = 0, l2_window_bytes = 0, l2_persist_bytes = 0;
     GvtSlot *d_slots = nullptr; GvtSlot **d_peer_slots = nullptr;      // my GVT mailbox; device copy of the peer table
 
@@ -391,7 +394,8 @@ struct Engine : EngineBase {
         TW_CUDA(cudaEventCreateWithFlags(&ev_chk[0], cudaEventDisableTiming));
         TW_CUDA(cudaEventCreateWithFlags(&ev_chk[1], cudaEventDisableTiming));
         TW_CUDA(cudaMalloc(&d.pages, nl * cap * sizeof(typename M::Event)));
-        TW_CUDA(cudaMalloc(&d.saved, nl * cap * sizeof(typename M::State)));
+        // saved pre-states (the UndoableLog) only for models that are not undone by reverse computation
+        TW_CUDA(cudaMalloc(&d.saved, (M::kReversible ? (size_t)1 : nl * cap) * sizeof(typename M::State)));
         // per-LP metadata in ONE allocation, hottest first: inbox counters | headers | model state.  An L2 persisting
         // window is laid over it below (the slot-reservation atomics and header reads then hit L2).
         auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -404,6 +408,12 @@ struct Engine : EngineBase {
         TW_CUDA(cudaMalloc(&d_tmp, 2 * sizeof(unsigned long long)));
         TW_CUDA(cudaHostAlloc(&h_ctl, 2 * sizeof(Ctl), cudaHostAllocDefault));
         grid = (int)((nl + kBlock - 1) / kBlock);
+        // tiles per warp: large partitions run several tiles per warp (fewer partial queue flushes and block epilogues),
+        // small ones keep one so that every SM gets work.  TWB200_TILES overrides.
+        // (measured on B200: c4 1M LPs 5.18 -> 5.53 G ev/s and c5 256K LPs 2.53 -> 2.77 with two tiles, 64K LPs slower)
+        d.tiles = nl >= (size_t)prop.multiProcessorCount * TW_MINBLOCKS * kBlock * 2 ? 2u : 1u;
+        if (const char *e = getenv("TWB200_TILES")) { const long v = atol(e); if (v >= 1 && v <= 64) d.tiles = (uint32_t)v; }
+        step_grid = (int)((nl + (size_t)kBlock * d.tiles - 1) / ((size_t)kBlock * d.tiles));
         TW_CUDA(cudaFuncSetAttribute(k_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
         // Keep the per-LP metadata resident in L2 with a persisting access-policy window (kernel nodes captured from
         // this stream inherit it).  TWB200_L2_WINDOW_MB overrides the size (0 = off); default = the inbox counters.
@@ -541,7 +551,7 @@ struct Engine : EngineBase {
         cudaGraph_t g = nullptr;
         TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         for (uint32_t i = 0; i < steps; ++i) {
-            k_step<M><<<grid, kBlock, stage_bytes(), stream>>>(d);
+            k_step<M><<<step_grid, kBlock, stage_bytes(), stream>>>(d);
             if (P.world > 1) {
                 if (getenv("TWB200_NCCL_GVT")) {         // fallback / comparison: ncclAllReduce(min) per super-step
                     int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);

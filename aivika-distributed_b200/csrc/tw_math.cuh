@@ -53,6 +53,18 @@ TW_HD uint64_t mix_fin(uint64_t z)
     z = (z ^ (z >> 27)) * kMulB;
     return z ^ (z >> 31);
 }
+// inverse of mix_fin (xor-shifts and odd multipliers are bijections of 64-bit words)
+constexpr uint64_t kMulAInv = 0x96DE1B173F119089ull;
+constexpr uint64_t kMulBInv = 0x319642B2D24D8EC3ull;
+TW_HD uint64_t mix_fin_inv(uint64_t z)
+{
+    z ^= z >> 31; z ^= z >> 62;
+    z *= kMulBInv;
+    z ^= z >> 27; z ^= z >> 54;
+    z *= kMulAInv;
+    z ^= z >> 30; z ^= z >> 60;
+    return z;
+}
 TW_HD uint64_t lp_stream_key(uint64_t seed, uint32_t lp) { return mix_fin(seed ^ (((uint64_t)lp + 1ull) * kGolden)); }
 TW_HD uint64_t stream_draw(uint64_t key, uint64_t ctr) { return mix_fin(key + ctr * kCtrMul); }
 
@@ -92,6 +104,13 @@ TW_HD uint64_t trace_fold(uint64_t h, double recv_ts, uint32_t src, uint64_t ctr
 {
     uint64_t x = d2bits(recv_ts) ^ (ctr * kMulB) ^ ((uint64_t)src * kMulA);
     return mix_fin((h ^ x) + kGolden);
+}
+
+// the fold is invertible: reverse computation restores the hash before an undone event
+TW_HD uint64_t trace_unfold(uint64_t h, double recv_ts, uint32_t src, uint64_t ctr)
+{
+    uint64_t x = d2bits(recv_ts) ^ (ctr * kMulB) ^ ((uint64_t)src * kMulA);
+    return (mix_fin_inv(h) - kGolden) ^ x;
 }
 
 // ---- StdGen (random-1.1: L'Ecuyer combined MLCG) ----

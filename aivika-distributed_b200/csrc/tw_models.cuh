@@ -11,6 +11,9 @@
 //   advance(params, lp, state, event) -> status   the sequential state transition of the LP (cheap, one LP = one lane)
 //   Work                                           what is needed to produce the messages of that execution
 //   emit(params, work, out[], n_out)               the messages themselves; pure, runs on whichever lane is free
+// A model with kReversible = true undoes an execution by reverse computation (reverse(params, lp, state, event) restores
+// the state before `event`), so the engine keeps no saved states for it: the UndoableLog (Internal/UndoableLog.hs)
+// shrinks to the processed event records themselves.  Otherwise the pre-state of every processed event is saved.
 // A model with kSplit = true derives Work from (pre-state, event) and does the heavy arithmetic in emit (PHOLD:
 // the draws, the logarithm and the destination); a model with kSplit = false computes its messages inside
 // handle() and a Work item is simply one finished message.
@@ -86,6 +89,12 @@ struct PholdModel {
         s.rng_ctr += 4; s.send_ctr += 1; s.n_exec += 1;
         return H_OK;
     }
+    static constexpr bool kReversible = true;
+    TW_HD static void reverse(const Params &, uint32_t, State &s, const Event &e)      // exact inverse of advance
+    {
+        s.hash = trace_unfold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
+        s.rng_ctr -= 4; s.send_ctr -= 1; s.n_exec -= 1;
+    }
     TW_HD static void emit(const Params &p, const Work &w, Event *out, int &n_out)
     {
         const uint32_t lp = w.lp;
@@ -140,6 +149,7 @@ struct PholdModel {
 struct MachRepModel {
     static constexpr int kMaxSends = 3;
     static constexpr bool kSplit = false;      // messages are computed inside handle(); a Work item is one finished message
+    static constexpr bool kReversible = false; // FCFS wait list, accumulators: the pre-state of every execution is saved
     struct alignas(16) Event {             // 48 B
         double   recv_ts, send_ts;
         uint64_t ctr;

@@ -31,15 +31,15 @@ ALGO_BYTES_MACHREP = 288
 WORKLOADS = {
     # name: (description, model kwargs, stop, default horizon, capacity, cpu-sample stop)
     "c4": dict(desc="PHOLD 1M LPs, 50% remote, P=16, lookahead 0.1, exp(1) delays, T=20 (BASELINE configs[3])",
-               kind="phold", n_lps=1 << 20, remote_pct=50, stop=20.0, horizon=0.2, cap=128, cpu_stop=0.5),
+               kind="phold", n_lps=1 << 20, remote_pct=50, stop=20.0, horizon=0.3, batch=6, cap=128, cpu_stop=0.5),
     "c3": dict(desc="PHOLD 64K LPs, 10% remote, P=16, lookahead 0.1, exp(1) delays, T=100 (BASELINE configs[2])",
-               kind="phold", n_lps=1 << 16, remote_pct=10, stop=100.0, horizon=0.2, cap=128, cpu_stop=10.0),
+               kind="phold", n_lps=1 << 16, remote_pct=10, stop=100.0, horizon=0.2, batch=6, cap=128, cpu_stop=10.0),
     "c5": dict(desc="rollback-heavy PHOLD 256K LPs, 50% remote, 10% of the remote messages to 4096 hot LPs "
-                    "(each hot LP holds ~7x the average event population), horizon 0.5, T=20 (BASELINE configs[4])",
-               kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10, stop=20.0, horizon=0.5, cap=512,
+                    "(each hot LP holds ~7x the average event population), T=20 (BASELINE configs[4])",
+               kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10, stop=20.0, horizon=0.3, batch=16, cap=512,
                cpu_stop=2.0),
     "c2": dict(desc="MachRep2DistributedReproducible replicated as 4096 independent 3-LP groups, stop 1000 (BASELINE configs[1])",
-               kind="machrep", n_replicas=4096, stop=1000.0, horizon=2.0, cap=256, cpu_stop=1000.0),
+               kind="machrep", n_replicas=4096, stop=1000.0, horizon=2.0, batch=4, cap=256, cpu_stop=1000.0),
 }
 
 
@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--horizon", type=float, default=None)
-    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cap", type=int, default=None)
     ap.add_argument("--stop", type=float, default=None)
     ap.add_argument("--steps-per-launch", type=int, default=16)
@@ -179,6 +179,8 @@ def main():
         wl["horizon"] = args.horizon
     if args.cap is not None:
         wl["cap"] = args.cap
+    if args.batch is None:
+        args.batch = wl["batch"]
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

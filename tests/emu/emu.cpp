@@ -40,7 +40,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         memset(&d, 0, sizeof d);
         d.n_global = p->n_lps; d.world = W; d.rank = r; d.n_per = n_per; d.lp_base = n_per * r;
         d.n_local = d.lp_base >= p->n_lps ? 0 : std::min(n_per, p->n_lps - d.lp_base);
-        d.cap = cap; d.mask = cap - 1;
+        d.cap = cap; d.mask = cap - 1; d.tiles = 1;
         d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : 8;
         d.proc_limit = p->proc_limit ? p->proc_limit : cap / 4;
         d.fossil_thresh = p->fossil_threshold ? p->fossil_threshold : cap / 8;
@@ -80,7 +80,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
         if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
         acc.init();
-        for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step & 1u); }
+        for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step); }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
         const double g = std::min(acc.pend_min, acc.emit_min);
         if (g < gvt) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", gvt, g, step); return 100; }
@@ -115,6 +115,23 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         }
     }
     return TW_OK;
+}
+
+// reverse computation: PholdModel::reverse must be the exact inverse of PholdModel::advance (returns mismatches)
+extern "C" int emu_phold_reverse_roundtrip(uint64_t seed, int n)
+{
+    int bad = 0; uint64_t s = seed;
+    PholdModel::Params p; memset(&p, 0, sizeof p);
+    for (int i = 0; i < n; ++i) {
+        PholdModel::State a; a.rng_ctr = rng_next(s); a.send_ctr = rng_next(s); a.n_exec = rng_next(s); a.hash = rng_next(s);
+        PholdModel::Event e; e.recv_ts = bits2d(rng_next(s) >> 2); e.send_ts = 0.0; e.ctr = rng_next(s); e.src = (uint32_t)rng_next(s); e.dst = 0;
+        PholdModel::State b = a;
+        PholdModel::advance(p, 7, b, e);
+        PholdModel::reverse(p, 7, b, e);
+        if (b.rng_ctr != a.rng_ctr || b.send_ctr != a.send_ctr || b.n_exec != a.n_exec || b.hash != a.hash) ++bad;
+        if (mix_fin_inv(mix_fin(a.hash)) != a.hash) ++bad;
+    }
+    return bad;
 }
 
 extern "C" int emu_run(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,

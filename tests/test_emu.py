@@ -21,7 +21,7 @@ def check_phold(H, p, seeds=(0, 1)):
 
 
 @pytest.mark.parametrize("horizon", [0.1, 0.5, 2.0, -1.0])
-@pytest.mark.parametrize("batch", [1, 4, 16, 64])
+@pytest.mark.parametrize("batch", [1, 4, 6, 16, 64])
 def test_phold_all_horizons_commit_the_sequential_schedule(H, horizon, batch):
     st_ = check_phold(H, H.phold_params(300, 6.0, remote_pct=40, horizon=horizon, batch=batch, cap=128 if batch <= 4 else 512))
     if horizon == 0.1:
@@ -97,7 +97,7 @@ def test_machrep2_partitioned_keeps_replicas_whole(H):
 
 @settings(max_examples=25, deadline=None)
 @given(n=st.integers(2, 200), pop=st.integers(1, 6), rp=st.integers(0, 100), hor=st.sampled_from([0.05, 0.3, 1.5, -1.0]),
-       batch=st.sampled_from([1, 2, 3, 4, 7, 16, 64]), seed=st.integers(0, 2 ** 32), world=st.sampled_from([1, 2, 4]), shuffle=st.integers(0, 99))
+       batch=st.sampled_from([1, 2, 3, 4, 6, 7, 16, 64]), seed=st.integers(0, 2 ** 32), world=st.sampled_from([1, 2, 4]), shuffle=st.integers(0, 99))
 def test_phold_random_configurations(H, n, pop, rp, hor, batch, seed, world, shuffle):
     p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hor, batch=batch, seed=seed, world=world, cap=128 if batch <= 4 else 512)
     check_phold(H, p, seeds=(shuffle,))
@@ -110,3 +110,8 @@ def test_phold_equal_timestamps_exercise_full_key_ordering(H):
         st_ = check_phold(H, H.phold_params(n, 3.0, population=pop, remote_pct=rp, lookahead=0.5, mean=0.0, horizon=hz,
                                             batch=batch, cap=512), seeds=(3,))
         assert st_.rolled_back > 0
+
+
+def test_phold_reverse_computation_is_the_exact_inverse(H):
+    """PHOLD is rolled back by reverse computation (no saved states): reverse(advance(s, e), e) == s for random words."""
+    assert H.emu().emu_phold_reverse_roundtrip(12345, 200000) == 0

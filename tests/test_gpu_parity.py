@@ -50,7 +50,7 @@ def test_phold_matches_oracle_for_every_horizon(H, horizon):
         assert st.rolled_back > 0 and 0 <= st.anti_sent - st.annihilated <= 64     # a few antis may still be in flight at the end
 
 
-@pytest.mark.parametrize("batch", [1, 2, 4, 8, 16, 64])
+@pytest.mark.parametrize("batch", [1, 2, 4, 6, 8, 16, 64])
 def test_phold_batch_sizes(H, batch):
     check_phold(H, H.phold_params(5000, 8.0, remote_pct=50, horizon=1.0, batch=batch, cap=128 if batch <= 4 else 512))
 
@@ -259,7 +259,7 @@ def test_random_phold_configurations(H):
     rng = np.random.default_rng(20261020)
     for _ in range(24):
         n = int(rng.integers(2, 3000)); pop = int(rng.integers(1, 9)); rp = int(rng.choice([0, 5, 50, 100]))
-        hz = float(rng.choice([0.05, 0.1, 0.35, 1.5, -1.0])); batch = int(rng.choice([1, 2, 3, 4, 8, 16, 64]))
+        hz = float(rng.choice([0.05, 0.1, 0.35, 1.5, -1.0])); batch = int(rng.choice([1, 2, 3, 4, 6, 8, 16, 64]))
         n_hot = int(rng.choice([0, 0, 7])); seed = int(rng.integers(0, 2 ** 31))
         p = H.phold_params(n, 4.0, population=pop, remote_pct=rp, horizon=hz, batch=batch, seed=seed,
                            n_hot=min(n_hot, n), hot_pct=5 if n_hot else 0, cap=1024, steps_per_launch=int(rng.choice([1, 4, 16])))

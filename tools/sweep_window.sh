@@ -1,5 +1,5 @@
 # usage: bash tools/sweep_window.sh  -- optimism window x batch sweep of the default library, then launch-shape variants
-# (aivika-distributed_b200/csrc/variants/lib_b<block>_m<minblocks>.so) at one operating point.  Prints one line per run.
+# (aivika-distributed_b200/csrc/variants/lib_b<block>_m<minblocks>_c<candidates>.so) at one operating point.
 run() {  # lib workload-args hz batch
   TWB200_LIB=$1 python bench.py --workload $2 --horizon $3 --batch $4 --steps 2 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
 import sys,json
@@ -9,7 +9,7 @@ try:
 except Exception as e: print('$1 $2 hz $3 batch $4 FAILED', t[:200])"
 }
 LIB=$PWD/aivika-distributed_b200/csrc/libtwb200.so
-for hz in 0.2 0.3 0.4 0.5 0.7; do for b in 4 8 16; do run $LIB "c4 --stop 5" $hz $b; done; done
-for hz in 0.2 0.3 0.5 0.7; do for b in 4 8 16; do run $LIB "c3 --stop 30" $hz $b; done; done
-for hz in 0.3 0.5 1.0; do for b in 4 8 16; do run $LIB "c5 --stop 5" $hz $b; done; done
-for v in aivika-distributed_b200/csrc/variants/lib_*.so; do run $PWD/$v "c4 --stop 5" 0.4 8; run $PWD/$v "c3 --stop 30" 0.4 8; done
+for hz in 0.2 0.3 0.4 0.5; do for b in 4 6 8 16; do run $LIB "c4 --stop 5" $hz $b; done; done
+for hz in 0.2 0.3; do for b in 4 6 8; do run $LIB "c3 --stop 30" $hz $b; done; done
+for hz in 0.3 0.5; do for b in 8 16 32; do run $LIB "c5 --stop 5" $hz $b; done; done
+for v in aivika-distributed_b200/csrc/variants/lib_*.so; do run $PWD/$v "c4 --stop 5" 0.3 8; run $PWD/$v "c3 --stop 30" 0.2 6; done
