@@ -10,7 +10,8 @@
 //   k_collect<M>  committed-event count and trace-hash sum
 // Multi-GPU: LP ranges are sharded (LP i lives on rank i / n_per); remote sends are direct NVLink peer
 // stores + peer atomics issued from inside k_step (no staging, no separate exchange kernel), and GVT is a
-// peer-memory mailbox exchange (k_gvt_exchange); NCCL is used for set-up and the collective host-side barriers only.
+// peer-memory mailbox exchange run by the last block of k_step (gvt_exchange_warp); NCCL is used for set-up and the
+// collective host-side barriers only.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -50,8 +51,55 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 
 enum { C_EXEC = 0, C_RB, C_ROLLBACKS, C_STRAG, C_ANTI, C_ANNIH, C_RETRY, C_SLOCAL, C_SREMOTE, C_FOSSIL, C_COUNT };
 
-// Block-level reduction of the per-thread accumulators, then the "last block" publishes GVT.
-__device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t step, uint32_t world, bool advance)
+// Cross-GPU GVT, run by one warp: every rank publishes its local minimum for step `tag` into the mailbox of every peer
+// (NVLink peer stores) and waits until all `world` entries for that step have arrived, then takes the minimum -- the
+// LocalTimeMessage / GlobalTimeMessage round of the Time Server (Internal/TimeServer.hs:253-270, 384-421) without a
+// server and without NCCL on the per-step path (an 8-byte ncclAllReduce costs ~20-40 us, this ~5 us).  It is also the
+// barrier that orders the peer stores of super-step s before the loads of super-step s+1.  Waits are bounded so that a
+// lost peer becomes an error code, never a hang.  One rank per GPU is required (and enforced by the host).
+__device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer_slots, uint32_t rank, uint32_t world,
+                                                  uint32_t tag, double local_min)
+{
+    const uint32_t r = threadIdx.x & 31u;
+    const uint32_t par = tag & 1u;
+    const bool aborted = *(volatile uint32_t *)&ctl->error != 0;
+    if (r < world) {
+        GvtSlot *dst = peer_slots[r] + par * kMaxWorld + rank;           // my entry in rank r's mailbox
+        if (aborted) {
+            *(volatile uint32_t *)&(peer_slots[r] + 0 * kMaxWorld + rank)->tag = kSlotAbort;
+            *(volatile uint32_t *)&(peer_slots[r] + 1 * kMaxWorld + rank)->tag = kSlotAbort;
+        } else {
+            *(volatile double *)&dst->value = local_min;
+            __threadfence_system();
+            *(volatile uint32_t *)&dst->tag = tag;
+        }
+    }
+    if (aborted) return;
+    double v = pos_inf(); uint32_t bad = 0;
+    if (r < world) {
+        const GvtSlot *src = peer_slots[rank] + par * kMaxWorld + r;      // rank r's entry in my mailbox
+        uint32_t t = *(volatile const uint32_t *)&src->tag, spins = 0;
+        while (t != tag) {
+            if (t == kSlotAbort) { bad = TW_ERR_CUDA; break; }
+            if (++spins > 4000000u) { bad = TW_ERR_DEADLOCK; break; }     // seconds: a peer is gone
+            __nanosleep(64);
+            t = *(volatile const uint32_t *)&src->tag;
+        }
+        __threadfence_system();
+        v = *(volatile const double *)&src->value;
+    }
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    const unsigned long long m = warp_min_u64(ordered_bits(v));
+    if (r == 0) {
+        if (bad) { if (atomicCAS(&ctl->error, 0u, bad) == 0u) ctl->err_lp = 0xFFFFFFFFu; }
+        else ctl->gvt = from_ordered(m);
+    }
+}
+
+// Block-level reduction of the per-thread accumulators, then the "last block" publishes GVT (and, in a multi-GPU run
+// with fused exchange, does the cross-GPU round itself: no separate kernel between two super-steps).
+__device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t step, uint32_t world, uint32_t rank,
+                                             GvtSlot *const *peer_slots, bool fused)
 {
     __shared__ unsigned long long s_pend[kBlock / 32], s_emit[kBlock / 32];
     __shared__ unsigned int s_cnt[C_COUNT];
@@ -85,18 +133,26 @@ __device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t 
         s_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long pm = *(volatile unsigned long long *)&ctl->pend_min;
-        const unsigned long long em = *(volatile unsigned long long *)&ctl->emit_min;
-        const double g = from_ordered(pm < em ? pm : em);
-        ctl->gvt_local = g;
-        if (world == 1) ctl->gvt = g;            // otherwise ncclAllReduce(min) gvt_local -> gvt follows on the stream
-        ctl->pend_min = ordered_bits(pos_inf());
-        ctl->emit_min = ordered_bits(pos_inf());
-        if (advance) { ctl->step = step + 1; ctl->c_steps += 1; }
-        ctl->done_blocks = 0;
-        __threadfence();
+    if (s_last && warp == 0) {
+        double g = 0.0;
+        if (lane == 0) {
+            __threadfence();
+            const unsigned long long pm = *(volatile unsigned long long *)&ctl->pend_min;
+            const unsigned long long em = *(volatile unsigned long long *)&ctl->emit_min;
+            g = from_ordered(pm < em ? pm : em);
+            ctl->gvt_local = g;
+            if (world == 1) ctl->gvt = g;            // otherwise the cross-GPU minimum follows
+            ctl->pend_min = ordered_bits(pos_inf());
+            ctl->emit_min = ordered_bits(pos_inf());
+            ctl->step = step + 1; ctl->c_steps += 1;
+            ctl->done_blocks = 0;
+            __threadfence();
+        }
+        __syncwarp();
+        if (world > 1 && fused) {
+            g = __shfl_sync(0xffffffffu, g, 0);
+            gvt_exchange_warp(ctl, peer_slots, rank, world, step + 1u, g);
+        }
     }
 }
 
@@ -111,16 +167,16 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
     double wend = d.stop;
     if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
-    extern __shared__ uint4 tw_queue_smem[];             // per warp: kQueueSlots work items (tw_core.cuh, WorkQ)
+    extern __shared__ uint4 tw_queue_smem[];             // per warp: work queue + held messages (tw_core.cuh, WorkQ)
     WorkQ<M> q;
-    q.init(reinterpret_cast<typename M::Work *>(tw_queue_smem) + (threadIdx.x >> 5) * kQueueSlots);
+    q.init(reinterpret_cast<char *>(tw_queue_smem) + (threadIdx.x >> 5) * WorkQ<M>::kWarpBytes);
     // one warp = d.tiles consecutive tiles of 32 LPs; the work queue is carried from tile to tile
     const uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
     for (uint32_t t = 0; t < d.tiles; ++t)
         lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
     q.drain(d, acc, step & 1u);
     if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
-    block_finish(ctl, acc, step, d.world, true);
+    block_finish(ctl, acc, step, d.world, d.rank, d.peer_slots, d.fused_gvt != 0u);
 }
 
 template <class M>
@@ -147,49 +203,11 @@ __global__ void __launch_bounds__(kBlock) k_route(const Dev<M> d, const tw_event
     }
 }
 
-// Cross-GPU GVT: every rank publishes its local minimum for step `tag` into the mailbox of every peer (NVLink peer
-// stores) and waits until all `world` entries for that step have arrived, then takes the minimum -- the
-// LocalTimeMessage / GlobalTimeMessage round of the Time Server (Internal/TimeServer.hs:253-270, 384-421) without a
-// server and without NCCL on the per-step path (an 8-byte ncclAllReduce costs ~20-40 us, this ~5 us).  It is also the
-// barrier that orders the peer stores of super-step s before the loads of super-step s+1.  One warp; waits are
-// bounded so that a lost peer becomes an error code, never a hang.  One rank per GPU is required (and enforced).
+// The same exchange as a kernel of its own (TWB200_GVT_KERNEL=1: comparison with the fused form).
 __global__ void k_gvt_exchange(Ctl *ctl, GvtSlot *const *peer_slots_dev, uint32_t rank, uint32_t world)
 {
-    const uint32_t r = threadIdx.x;
     const uint32_t tag = *(volatile uint32_t *)&ctl->step;
-    const uint32_t par = tag & 1u;
-    const bool aborted = *(volatile uint32_t *)&ctl->error != 0;
-    if (r < world) {
-        GvtSlot *dst = peer_slots_dev[r] + par * kMaxWorld + rank;       // my entry in rank r's mailbox
-        if (aborted) {
-            *(volatile uint32_t *)&(peer_slots_dev[r] + 0 * kMaxWorld + rank)->tag = kSlotAbort;
-            *(volatile uint32_t *)&(peer_slots_dev[r] + 1 * kMaxWorld + rank)->tag = kSlotAbort;
-        } else {
-            *(volatile double *)&dst->value = *(volatile double *)&ctl->gvt_local;
-            __threadfence_system();
-            *(volatile uint32_t *)&dst->tag = tag;
-        }
-    }
-    if (aborted) return;
-    double v = pos_inf(); uint32_t bad = 0;
-    if (r < world) {
-        const GvtSlot *src = peer_slots_dev[rank] + par * kMaxWorld + r;  // rank r's entry in my mailbox
-        uint32_t t = *(volatile const uint32_t *)&src->tag, spins = 0;
-        while (t != tag) {
-            if (t == kSlotAbort) { bad = TW_ERR_CUDA; break; }
-            if (++spins > 4000000u) { bad = TW_ERR_DEADLOCK; break; }     // seconds: a peer is gone
-            __nanosleep(64);
-            t = *(volatile const uint32_t *)&src->tag;
-        }
-        __threadfence_system();
-        v = *(volatile const double *)&src->value;
-    }
-    bad = __reduce_max_sync(0xffffffffu, bad);
-    const unsigned long long m = warp_min_u64(ordered_bits(v));
-    if (r == 0) {
-        if (bad) { if (atomicCAS(&ctl->error, 0u, bad) == 0u) ctl->err_lp = 0xFFFFFFFFu; }
-        else ctl->gvt = from_ordered(m);
-    }
+    gvt_exchange_warp(ctl, peer_slots_dev, rank, world, tag, *(volatile double *)&ctl->gvt_local);
 }
 
 // after k_route: gvt = min(gvt, injected minimum)   (single thread)
@@ -439,12 +457,14 @@ struct Engine : EngineBase {
             }
         }
         d.peer_pages[d.rank] = d.pages; d.peer_in[d.rank] = d.in;
+        // multi-GPU GVT: fused into k_step's last block unless a comparison mode is requested
+        d.fused_gvt = (p.world > 1 && !getenv("TWB200_GVT_KERNEL") && !getenv("TWB200_NCCL_GVT")) ? 1u : 0u;
         if (p.world > 1) { int rc = init_peers(); if (rc) return rc; }
         return reset();
     }
 
     // exchange cudaIpc handles of pages / inbox counters through NCCL and map every peer (NVLink P2P)
-    static size_t stage_bytes() { return (size_t)(kBlock / 32) * kQueueSlots * sizeof(typename M::Work); }   // work queues
+    static size_t stage_bytes() { return (size_t)(kBlock / 32) * WorkQ<M>::kWarpBytes; }   // work queues + held messages
 
     int init_peers()
     {
@@ -552,7 +572,7 @@ struct Engine : EngineBase {
         TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         for (uint32_t i = 0; i < steps; ++i) {
             k_step<M><<<step_grid, kBlock, stage_bytes(), stream>>>(d);
-            if (P.world > 1) {
+            if (P.world > 1 && !d.fused_gvt) {
                 if (getenv("TWB200_NCCL_GVT")) {         // fallback / comparison: ncclAllReduce(min) per super-step
                     int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);
                     if (e) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); err = "ncclAllReduce failed during capture"; return TW_ERR_CUDA; }
@@ -586,7 +606,7 @@ struct Engine : EngineBase {
         double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
         Ctl last = c0;
         while (!finished) {
-            TW_CUDA(cudaGraphLaunch(graph, stream)); count(P.world > 1 ? 2 * B : B);
+            TW_CUDA(cudaGraphLaunch(graph, stream)); count((P.world > 1 && !d.fused_gvt) ? 2 * B : B);
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             TW_CUDA(cudaEventRecord(ev_chk[slot], stream));
             pending[slot] = true;

@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--cap", type=int, default=None)
     ap.add_argument("--stop", type=float, default=None)
+    ap.add_argument("--n-lps", type=int, default=None, help="diagnostic: override the LP count of a PHOLD workload")
+    ap.add_argument("--remote-pct", type=int, default=None, help="diagnostic: override the remote share of a PHOLD workload")
     ap.add_argument("--steps-per-launch", type=int, default=16)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -181,6 +183,12 @@ def main():
         wl["cap"] = args.cap
     if args.batch is None:
         args.batch = wl["batch"]
+    if args.n_lps is not None or args.remote_pct is not None:
+        if args.n_lps is not None:
+            wl["n_lps"] = args.n_lps
+        if args.remote_pct is not None:
+            wl["remote_pct"] = args.remote_pct
+        wl["desc"] += f" [diagnostic override: n_lps={wl['n_lps']}, remote_pct={wl['remote_pct']}]"
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -273,7 +281,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None        # DRAM bytes per k_step launch from the committed ncu --set full capture of this workload
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
         steps_per_run = stats[-1]["steps"]

@@ -99,7 +99,7 @@ typedef struct tw_params {
     uint32_t rank, world;         /* this partition / number of partitions (GPUs); LP i lives on i / ceil(n_lps/world) */
     int32_t  device;              /* CUDA device ordinal, -1 = current */
     uint32_t queue_capacity;      /* per-LP slots (power of two); ~ dioUndoableLogSizeThreshold / dioOutputMessageQueueSizeThreshold */
-    uint32_t max_events_per_step; /* optimistic batch per LP per super-step, 1..4 (0 = 4) */
+    uint32_t max_events_per_step; /* optimistic batch per LP per super-step, 1..64 (0 = 8) */
     uint32_t steps_per_launch;    /* super-steps per graph launch between host GVT checks */
     double   start_time;          /* spcStartTime */
     double   stop_time;           /* spcStopTime (inclusive, Internal/Event.hs:228-229) */

@@ -18,9 +18,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cases = [
-        ("phold optimistic", D.PHOLD(30011, remote_pct=50, seed=3), D.DIOParams(dioTimeHorizon=0.7), 6.0),
+        ("phold optimistic", D.PHOLD(30011, remote_pct=50, seed=3), D.DIOParams(dioTimeHorizon=0.7, maxEventsPerStep=8, queueCapacity=256), 6.0),
         ("phold unbounded", D.PHOLD(4096, population=4, remote_pct=100, seed=9), D.DIOParams(dioTimeHorizon=None), 5.0),
-        ("phold skewed", D.PHOLD(20000, remote_pct=50, n_hot=256, hot_pct=20, seed=5), D.DIOParams(dioTimeHorizon=0.5, queueCapacity=512), 4.0),
+        ("phold skewed", D.PHOLD(20000, remote_pct=50, n_hot=256, hot_pct=20, seed=5), D.DIOParams(dioTimeHorizon=0.5, queueCapacity=512, maxEventsPerStep=16), 4.0),
         ("machrep2", D.MachRep2(257), D.DIOParams(queueCapacity=64, stepsPerLaunch=32), 200.0),
     ]
     ok = True
