@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtwb200.so")
 TW_OK = 0
 TW_MODEL_PHOLD = 1
 TW_MODEL_MACHREP2 = 2
+TW_MODEL_MACHREP1 = 3
 
 ERROR_NAMES = {
     0: "TW_OK", 1: "TW_ERR_INVALID_ARG", 2: "TW_ERR_CUDA", 3: "TW_ERR_SEND_AFTER_RECV",

@@ -260,20 +260,16 @@ __global__ void __launch_bounds__(kBlock) k_gather_stats(const Dev<M> d, unsigne
     n_exec[l] = d.state[l].n_exec; hash[l] = d.state[l].hash;
 }
 
-__global__ void k_gather_machrep(const Dev<MachRepModel> d, tw_machrep_result *out, uint32_t n_rep, double t_stop)
+template <class M>
+__global__ void k_gather_replicas(const Dev<M> d, tw_machrep_result *out, uint32_t n_rep, double t_stop)
 {
     const uint32_t r = blockIdx.x * kBlock + threadIdx.x;
     if (r >= n_rep) return;
-    // masters owned by this partition, in order
-    const uint32_t first_master = ((d.lp_base + 2u) / 3u) * 3u;
-    const uint32_t lp = first_master + 3u * r;
+    // masters (first LP of each group) owned by this partition, in order
+    const uint32_t first_master = ((d.lp_base + M::kGroup - 1u) / M::kGroup) * M::kGroup;
+    const uint32_t lp = first_master + M::kGroup * r;
     if (lp < d.lp_base || lp >= d.lp_base + d.n_local) return;
-    const MachRepModel::State s = d.state[lp - d.lp_base];
-    tw_machrep_result o;
-    o.total_up_time = s.total_up_time; o.n_rep = s.n_rep; o.n_immed_rep = s.n_immed;
-    o.up_time_prop = s.total_up_time / (2.0 * t_stop);              // tests/MachRep2DistributedReproducible.hs:214-217
-    o.immed_prop = (double)s.n_immed / (double)s.n_rep;              // :219-224
-    out[r] = o;
+    out[r] = M::result(d.state[lp - d.lp_base], t_stop);
 }
 
 // ------------------------------------------------------------------ NCCL through dlopen (torch-bundled or system libnccl.so.2)
@@ -397,7 +393,7 @@ struct Engine : EngineBase {
         memset(&d, 0, sizeof d);
         d.n_global = p.n_lps; d.world = p.world; d.rank = p.rank;
         d.n_per = (p.n_lps + p.world - 1) / p.world;
-        if (std::is_same<M, MachRepModel>::value && p.world > 1) d.n_per = ((d.n_per + 2) / 3) * 3;   // keep replicas whole
+        if (M::kGroup > 1 && p.world > 1) d.n_per = ((d.n_per + M::kGroup - 1) / M::kGroup) * M::kGroup;   // keep replicas whole
         d.lp_base = d.n_per * p.rank;
         d.n_local = d.lp_base >= p.n_lps ? 0 : (p.n_lps - d.lp_base < d.n_per ? p.n_lps - d.lp_base : d.n_per);
         d.cap = cap; d.mask = cap - 1; d.max_batch = mb;
@@ -716,21 +712,44 @@ struct Engine : EngineBase {
     }
 };
 
-template <> int Engine<PholdModel>::read_machrep(tw_machrep_result *, size_t) { err = "not a MachRep2 engine"; return TW_ERR_NOT_SUPPORTED; }
-template <> int Engine<MachRepModel>::read_machrep(tw_machrep_result *out, size_t n)
+template <class M>
+int Engine<M>::read_machrep(tw_machrep_result *out, size_t n)
 {
-    const uint32_t first_master = ((d.lp_base + 2u) / 3u) * 3u;
-    const uint32_t end = d.lp_base + d.n_local;
-    const uint32_t n_rep = first_master < end ? (end - first_master + 2u) / 3u : 0u;
-    if (n < n_rep) { err = "output array shorter than the local replica count"; return TW_ERR_INVALID_ARG; }
-    if (!n_rep) return TW_OK;
-    tw_machrep_result *dr = nullptr;
-    TW_CUDA(cudaMalloc(&dr, sizeof(tw_machrep_result) * n_rep));
-    k_gather_machrep<<<(n_rep + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, dr, n_rep, P.stop_time); count(1);
-    TW_CUDA(cudaMemcpyAsync(out, dr, sizeof(tw_machrep_result) * n_rep, cudaMemcpyDeviceToHost, stream));
-    TW_CUDA(cudaStreamSynchronize(stream));
-    TW_CUDA(cudaFree(dr));
-    return TW_OK;
+    if constexpr (M::kGroup == 1) { (void)out; (void)n; err = "this model has no per-replica result"; return TW_ERR_NOT_SUPPORTED; }
+    else {
+        const uint32_t first_master = ((d.lp_base + M::kGroup - 1u) / M::kGroup) * M::kGroup;
+        const uint32_t end = d.lp_base + d.n_local;
+        const uint32_t n_rep = first_master < end ? (end - first_master + M::kGroup - 1u) / M::kGroup : 0u;
+        if (n < n_rep) { err = "output array shorter than the local replica count"; return TW_ERR_INVALID_ARG; }
+        if (!n_rep) return TW_OK;
+        tw_machrep_result *dr = nullptr;
+        TW_CUDA(cudaMalloc(&dr, sizeof(tw_machrep_result) * n_rep));
+        k_gather_replicas<M><<<(n_rep + kBlock - 1) / kBlock, kBlock, 0, stream>>>(d, dr, n_rep, P.stop_time); count(1);
+        TW_CUDA(cudaMemcpyAsync(out, dr, sizeof(tw_machrep_result) * n_rep, cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        TW_CUDA(cudaFree(dr));
+        return TW_OK;
+    }
+}
+
+// ------------------------------------------------------------------ the handler table
+// One row per compiled model: a model is a struct of tw_models.cuh (State, Event payload, handle or advance/emit, built
+// from the primitives of tw_dsl.cuh); registering it here is all the engine needs.
+struct ModelEntry {
+    uint32_t id; const char *name; uint32_t group;
+    EngineBase *(*make)(const tw_params &, int *rc);
+    size_t (*initial_events)(const tw_params &, tw_event *, size_t, uint32_t, uint32_t);
+};
+template <class M> static EngineBase *make_engine(const tw_params &p, int *rc) { auto *e = new Engine<M>(); *rc = e->init(p); return e; }
+static const ModelEntry kModels[] = {
+    {TW_MODEL_PHOLD,    "PHOLD",    PholdModel::kGroup,    make_engine<PholdModel>,    PholdModel::initial_events},
+    {TW_MODEL_MACHREP2, "MachRep2", MachRepModel::kGroup,  make_engine<MachRepModel>,  MachRepModel::initial_events},
+    {TW_MODEL_MACHREP1, "MachRep1", MachRep1Model::kGroup, make_engine<MachRep1Model>, MachRep1Model::initial_events},
+};
+static const ModelEntry *find_model(uint32_t id)
+{
+    for (const ModelEntry &m : kModels) if (m.id == id) return &m;
+    return nullptr;
 }
 
 }  // namespace twb
@@ -748,12 +767,11 @@ int tw_create(const tw_params *p, tw_engine **out)
 {
     if (!p || !out) return TW_ERR_INVALID_ARG;
     *out = nullptr;
-    EngineBase *impl = nullptr; int rc;
-    if (p->model == TW_MODEL_PHOLD) { auto *e = new Engine<PholdModel>(); rc = e->init(*p); impl = e; }
-    else if (p->model == TW_MODEL_MACHREP2) {
-        if (p->n_lps % 3u) { g_create_err = "MachRep2 needs n_lps = 3 * replicas"; return TW_ERR_INVALID_ARG; }
-        auto *e = new Engine<MachRepModel>(); rc = e->init(*p); impl = e;
-    } else { g_create_err = "unknown model"; return TW_ERR_INVALID_ARG; }
+    const ModelEntry *m = find_model(p->model);
+    if (!m) { g_create_err = "unknown model"; return TW_ERR_INVALID_ARG; }
+    if (p->n_lps % m->group) { g_create_err = std::string(m->name) + " needs n_lps = " + std::to_string(m->group) + " * replicas"; return TW_ERR_INVALID_ARG; }
+    int rc = TW_OK;
+    EngineBase *impl = m->make(*p, &rc);
     if (rc != TW_OK) { g_create_err = impl->err; delete impl; return rc; }
     tw_engine *h = new tw_engine(); h->impl = impl; *out = h;
     return TW_OK;
@@ -773,18 +791,18 @@ int tw_partition(const tw_engine *e, uint32_t *base, uint32_t *n) { if (!e) retu
 int tw_model_initial_events(const tw_params *p, tw_event *out, size_t cap, size_t *n)
 {
     if (!p || !out || !n) return TW_ERR_INVALID_ARG;
-    if (p->model == TW_MODEL_PHOLD) *n = PholdModel::initial_events(*p, out, cap);
-    else if (p->model == TW_MODEL_MACHREP2) *n = MachRepModel::initial_events(*p, out, cap);
-    else return TW_ERR_INVALID_ARG;
+    const ModelEntry *m = find_model(p->model);
+    if (!m) return TW_ERR_INVALID_ARG;
+    *n = m->initial_events(*p, out, cap, 0u, 0xFFFFFFFFu);
     return TW_OK;
 }
 
 int tw_model_initial_events_range(const tw_params *p, uint32_t lp0, uint32_t lp1, tw_event *out, size_t cap, size_t *n)
 {
     if (!p || !out || !n) return TW_ERR_INVALID_ARG;
-    if (p->model == TW_MODEL_PHOLD) *n = PholdModel::initial_events(*p, out, cap, lp0, lp1);
-    else if (p->model == TW_MODEL_MACHREP2) *n = MachRepModel::initial_events(*p, out, cap, lp0, lp1);
-    else return TW_ERR_INVALID_ARG;
+    const ModelEntry *m = find_model(p->model);
+    if (!m) return TW_ERR_INVALID_ARG;
+    *n = m->initial_events(*p, out, cap, lp0, lp1);
     return TW_OK;
 }
 

@@ -22,7 +22,7 @@
 // invariant, unlike generateMessageSequenceNo, Internal/OutputMessageQueue.hs:119-122),
 // bit 63 = anti-message toggle (Internal/Message.hs:48), bit 62 = annihilated, bit 61 = processed as no-op.
 #pragma once
-#include "tw_math.cuh"
+#include "tw_dsl.cuh"
 #include "../../include/twb200.h"
 
 namespace twb {
@@ -32,11 +32,10 @@ constexpr uint64_t kDeadBit = 1ull << 62;
 constexpr uint64_t kNoopBit = 1ull << 61;
 constexpr uint64_t kCtrMask = ~(kAntiBit | kDeadBit | kNoopBit);
 
-enum HandlerStatus { H_OK = 0, H_RETRY = 1, H_BAD = 2 };
-
 // ------------------------------------------------------------------ PHOLD
 struct PholdModel {
     static constexpr int kMaxSends = 1;
+    static constexpr uint32_t kGroup = 1;
     struct alignas(32) Event {             // 32 B: one DRAM sector
         double   recv_ts, send_ts;
         uint64_t ctr;
@@ -161,9 +160,7 @@ struct MachRepModel {
     struct alignas(16) State {             // 64 B; master and slave views share the record
         double   total_up_time;            // master :167
         int64_t  n_rep, n_immed;           // master :168-169
-        int32_t  count;                    // master: resourceCount of the FCFS repairPerson (:171-172)
-        uint8_t  wait[3];                  // master: FCFS wait list (Optimistic/QueueStrategy.hs:24-45)
-        uint8_t  wait_len;
+        dsl::FcfsResource<3> repair_person;    // master: newFCFSResource 1 (:171-172), tw_dsl.cuh
         StdGen   gen;                      // slave: Ref DIO StdGen (:77-78), rolled back with the state
         uint64_t send_ctr, n_exec, hash;
     };
@@ -181,8 +178,7 @@ struct MachRepModel {
     TW_HD static State initial_state(const Params &p, uint32_t lp)
     {
         State s;
-        s.total_up_time = 0.0; s.n_rep = 0; s.n_immed = 0; s.count = 1; s.wait_len = 0;
-        s.wait[0] = s.wait[1] = s.wait[2] = 0;
+        s.total_up_time = 0.0; s.n_rep = 0; s.n_immed = 0; s.repair_person.init(1);
         const uint32_t role = lp % 3u, r = lp / 3u;
         s.gen.s1 = 0; s.gen.s2 = 0;
         if (role == 1) s.gen = mk_std_gen(p.seed1 + (int64_t)r * p.stride);
@@ -200,34 +196,29 @@ struct MachRepModel {
     }
     TW_HD static uint32_t work_lp(const Event &w) { return w.src; }
     TW_HD static void emit(const Params &, const Event &w, Event *out, int &n_out) { out[0] = w; n_out = 1; }
-    TW_HD static void send(State &s, uint32_t from, uint32_t to, double now, double at, uint32_t type, double value,
-                           Event *out, int &n_out)
-    {
-        Event &o = out[n_out++];
-        o.recv_ts = at; o.send_ts = now; o.ctr = s.send_ctr++; o.src = from; o.dst = to; o.type = type; o.pad = 0; o.value = value;
-    }
     TW_HD static int handle(const Params &p, uint32_t lp, State &s, const Event &e, Event *out, int &n_out)
     {
         const uint32_t role = lp % 3u, master = lp - role;
         const double t = e.recv_ts, td = fadd(t, p.delta);
         n_out = 0;
+        dsl::Outbox<Event> ob(out, n_out, s.send_ctr, lp, t);
         if (role != 0) {
             switch (e.type) {
             case TW_MR_START:
             case TW_MR_RELEASE_REPAIR_PERSON_RESP: {          // machine, :130-135 / :150-154
-                const double up = expo_variate(std_random_double(s.gen), p.mean_up);
+                const double up = dsl::random_exponential(s.gen, p.mean_up);
                 const double at = fadd(td, up);
-                send(s, lp, master, t, at, TW_MR_TOTAL_UP_TIME_CHANGE, up, out, n_out);
-                send(s, lp, master, t, at, TW_MR_NREP_CHANGE, 1.0, out, n_out);
-                send(s, lp, master, t, at, TW_MR_REPAIR_PERSON_COUNT, 0.0, out, n_out);
+                ob.enqueueMessage(master, at, TW_MR_TOTAL_UP_TIME_CHANGE, up);
+                ob.enqueueMessage(master, at, TW_MR_NREP_CHANGE, 1.0);
+                ob.enqueueMessage(master, at, TW_MR_REPAIR_PERSON_COUNT, 0.0);
                 break; }
             case TW_MR_REPAIR_PERSON_COUNT_RESP:              // :137-142
-                if ((int64_t)e.value == 1) send(s, lp, master, t, td, TW_MR_NIMMED_REP_CHANGE, 1.0, out, n_out);
-                send(s, lp, master, t, td, TW_MR_REQUEST_REPAIR_PERSON, 0.0, out, n_out);
+                if ((int64_t)e.value == 1) ob.enqueueMessage(master, td, TW_MR_NIMMED_REP_CHANGE, 1.0);
+                ob.enqueueMessage(master, td, TW_MR_REQUEST_REPAIR_PERSON, 0.0);
                 break;
             case TW_MR_REQUEST_REPAIR_PERSON_RESP: {          // :144-148
-                const double rt = expo_variate(std_random_double(s.gen), p.mean_rep);
-                send(s, lp, master, t, fadd(td, rt), TW_MR_RELEASE_REPAIR_PERSON, 0.0, out, n_out);
+                const double rt = dsl::random_exponential(s.gen, p.mean_rep);
+                ob.enqueueMessage(master, fadd(td, rt), TW_MR_RELEASE_REPAIR_PERSON, 0.0);
                 break; }
             default: break;                                    // responses nobody subscribed to
             }
@@ -236,35 +227,25 @@ struct MachRepModel {
             switch (e.type) {
             case TW_MR_TOTAL_UP_TIME_CHANGE:                  // :176-180
                 s.total_up_time = fadd(s.total_up_time, e.value);
-                send(s, lp, from, t, td, TW_MR_TOTAL_UP_TIME_CHANGE_RESP, 0.0, out, n_out); break;
+                ob.enqueueMessage(from, td, TW_MR_TOTAL_UP_TIME_CHANGE_RESP, 0.0); break;
             case TW_MR_NREP_CHANGE:                           // :182-186
                 s.n_rep += (int64_t)e.value;
-                send(s, lp, from, t, td, TW_MR_NREP_CHANGE_RESP, 0.0, out, n_out); break;
+                ob.enqueueMessage(from, td, TW_MR_NREP_CHANGE_RESP, 0.0); break;
             case TW_MR_NIMMED_REP_CHANGE:                     // :188-192
                 s.n_immed += (int64_t)e.value;
-                send(s, lp, from, t, td, TW_MR_NIMMED_REP_CHANGE_RESP, 0.0, out, n_out); break;
+                ob.enqueueMessage(from, td, TW_MR_NIMMED_REP_CHANGE_RESP, 0.0); break;
             case TW_MR_REPAIR_PERSON_COUNT:                   // :194-198
-                send(s, lp, from, t, td, TW_MR_REPAIR_PERSON_COUNT_RESP, (double)s.count, out, n_out); break;
-            case TW_MR_REQUEST_REPAIR_PERSON:                 // :200-206 requestResource
-                if (s.count == 0) {
-                    if (s.wait_len >= 3) return H_RETRY;       // only reachable from a stale optimistic state
-                    s.wait[s.wait_len++] = (uint8_t)(from - master);
-                } else {
-                    s.count -= 1;
-                    send(s, lp, from, t, td, TW_MR_REQUEST_REPAIR_PERSON_RESP, 0.0, out, n_out);
-                }
-                break;
+                ob.enqueueMessage(from, td, TW_MR_REPAIR_PERSON_COUNT_RESP, (double)s.repair_person.count); break;
+            case TW_MR_REQUEST_REPAIR_PERSON: {               // :200-206 requestResource
+                bool granted;
+                if (s.repair_person.request((uint8_t)(from - master), granted) != H_OK) return H_RETRY;
+                if (granted) ob.enqueueMessage(from, td, TW_MR_REQUEST_REPAIR_PERSON_RESP, 0.0);
+                break; }
             case TW_MR_RELEASE_REPAIR_PERSON: {               // :208-212 releaseResourceWithinEvent
-                const int32_t c1 = s.count + 1;
-                if (c1 > 1) return H_RETRY;                    // SimulationRetry (Internal/Event.hs:247-249, 768-813)
-                uint32_t waiter = 0; bool resumed = false;
-                if (s.wait_len == 0) s.count = c1;
-                else {
-                    waiter = master + s.wait[0]; resumed = true;
-                    s.wait[0] = s.wait[1]; s.wait[1] = s.wait[2]; s.wait[2] = 0; s.wait_len--;
-                }
-                send(s, lp, from, t, td, TW_MR_RELEASE_REPAIR_PERSON_RESP, 0.0, out, n_out);
-                if (resumed) send(s, lp, waiter, t, td, TW_MR_REQUEST_REPAIR_PERSON_RESP, 0.0, out, n_out);
+                bool resumed; uint8_t w;
+                if (s.repair_person.release(1, resumed, w) != H_OK) return H_RETRY;   // SimulationRetry (Internal/Event.hs:247-249, 768-813)
+                ob.enqueueMessage(from, td, TW_MR_RELEASE_REPAIR_PERSON_RESP, 0.0);
+                if (resumed) ob.enqueueMessage(master + w, td, TW_MR_REQUEST_REPAIR_PERSON_RESP, 0.0);
                 break; }
             default: break;
             }
@@ -272,6 +253,15 @@ struct MachRepModel {
         s.hash = trace_fold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
         if (e.type != TW_MR_START) s.n_exec += 1;
         return H_OK;
+    }
+    static constexpr uint32_t kGroup = 3;      // LPs of one closed group (kept on one GPU)
+    TW_HD static tw_machrep_result result(const State &s, double t_stop)
+    {
+        tw_machrep_result o;
+        o.total_up_time = s.total_up_time; o.n_rep = s.n_rep; o.n_immed_rep = s.n_immed;
+        o.up_time_prop = s.total_up_time / (2.0 * t_stop);             // tests/MachRep2DistributedReproducible.hs:214-217
+        o.immed_prop = (double)s.n_immed / (double)s.n_rep;            // :219-224
+        return o;
     }
     static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
@@ -282,6 +272,93 @@ struct MachRepModel {
             tw_event &e = out[n++];
             e.recv_ts = tp.start_time; e.send_ts = tp.start_time; e.ctr = 0; e.src = lp; e.dst = lp;
             e.type = TW_MR_START; e.pad = 0; e.value = 0.0;
+        }
+        return n;
+    }
+};
+
+// ------------------------------------------------------------------ MachRep1
+// tests/MachRep1.hs: two machines and two repair persons (no contention).  LP 3r = masterModel (:75-93), LP 3r+1 / 3r+2 =
+// slaveModel (:52-72) of replica r.  The `machine` process becomes three self-scheduled events (holdProcess =
+// enqueueEvent at now + dt): START / REPAIR_END draw the up time, UP_END reports it to the master with sendMessage
+// (receive time = now: no lookahead at all) and draws the repair time.  The reference draws from the run's default
+// generator (not reproducible); here each slave owns a StdGen like tests/MachRep2Reproducible.hs:58-67.
+struct MachRep1Model {
+    static constexpr int kMaxSends = 2;
+    static constexpr bool kSplit = false;
+    static constexpr bool kReversible = false;
+    static constexpr uint32_t kGroup = 3;
+    using Event = MachRepModel::Event;
+    using Work = Event;
+    using Params = MachRepModel::Params;
+    struct alignas(16) State {             // 48 B
+        double   total_up_time;            // master: Ref totalUpTime (:78)
+        int64_t  n_rep;                    // master: messages received (not in the reference; a check value)
+        StdGen   gen;                      // slave
+        uint64_t send_ctr, n_exec, hash;
+    };
+    static Params make_params(const tw_params &p) { return MachRepModel::make_params(p); }
+    TW_HD static State initial_state(const Params &p, uint32_t lp)
+    {
+        State s;
+        s.total_up_time = 0.0; s.n_rep = 0;
+        const uint32_t role = lp % 3u, r = lp / 3u;
+        s.gen.s1 = 0; s.gen.s2 = 0;
+        if (role == 1) s.gen = mk_std_gen(p.seed1 + (int64_t)r * p.stride);
+        if (role == 2) s.gen = mk_std_gen(p.seed2 + (int64_t)r * p.stride);
+        s.send_ctr = role ? 1ull : 0ull;   // slaves: ctr 0 is the START self-event
+        s.n_exec = 0;
+        s.hash = mix_fin(lp_stream_key(0, lp) + 1ull);
+        return s;
+    }
+    TW_HD static Event from_wire(const tw_event &w) { return MachRepModel::from_wire(w); }
+    TW_HD static uint32_t work_lp(const Event &w) { return w.src; }
+    TW_HD static void emit(const Params &, const Event &w, Event *out, int &n_out) { out[0] = w; n_out = 1; }
+    TW_HD static int handle(const Params &p, uint32_t lp, State &s, const Event &e, Event *out, int &n_out)
+    {
+        const uint32_t role = lp % 3u, master = lp - role;
+        const double t = e.recv_ts;
+        n_out = 0;
+        dsl::Outbox<Event> ob(out, n_out, s.send_ctr, lp, t);
+        if (role != 0) {
+            switch (e.type) {
+            case TW_M1_START:
+            case TW_M1_REPAIR_END: {                           // machine :55-58: upTime <- randomExponential; holdProcess upTime
+                const double up = dsl::random_exponential(s.gen, p.mean_up);
+                ob.enqueueMessage(lp, fadd(t, up), TW_M1_UP_END, up);
+                break; }
+            case TW_M1_UP_END: {                               // :60-66: sendMessage masterId (TotalUpTimeChange upTime); repair
+                ob.sendMessage(master, TW_M1_TOTAL_UP_TIME_CHANGE, e.value);
+                const double rt = dsl::random_exponential(s.gen, p.mean_rep);
+                ob.enqueueMessage(lp, fadd(t, rt), TW_M1_REPAIR_END, 0.0);
+                break; }
+            default: break;
+            }
+        } else if (e.type == TW_M1_TOTAL_UP_TIME_CHANGE) {     // :84-86: modifyRef totalUpTime (+ x)
+            s.total_up_time = fadd(s.total_up_time, e.value);
+            s.n_rep += 1;
+        }
+        s.hash = trace_fold(s.hash, e.recv_ts, e.src, e.ctr & kCtrMask);
+        if (e.type != TW_M1_START) s.n_exec += 1;
+        return H_OK;
+    }
+    TW_HD static tw_machrep_result result(const State &s, double t_stop)
+    {
+        tw_machrep_result o;
+        o.total_up_time = s.total_up_time; o.n_rep = s.n_rep; o.n_immed_rep = 0;
+        o.up_time_prop = s.total_up_time / (2.0 * t_stop);             // tests/MachRep1.hs:88-91, n = 2
+        o.immed_prop = 0.0;
+        return o;
+    }
+    static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
+    {
+        size_t n = 0;
+        for (uint32_t lp = lp0; lp < tp.n_lps && lp < lp1; ++lp) {
+            if (lp % 3u == 0) continue;                        // runProcessInStartTime machine, :68
+            if (n >= cap) return n;
+            tw_event &e = out[n++];
+            e.recv_ts = tp.start_time; e.send_ts = tp.start_time; e.ctr = 0; e.src = lp; e.dst = lp;
+            e.type = TW_M1_START; e.pad = 0; e.value = 0.0;
         }
         return n;
     }

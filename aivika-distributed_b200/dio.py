@@ -8,7 +8,7 @@ Names, argument meaning and error behaviour follow the reference (paths relative
   timeServer / TimeServerParams  Internal/TimeServer.hs:47-72, 485
   LogicalProcessState            Optimistic/State.hs:27-54
 The reference runs one Haskell closure per event; the device runs a *compiled* handler for a whole batch of
-homogeneous LPs, so a run is described by a model descriptor (PHOLD / MachRep2) instead of a closure.
+homogeneous LPs, so a run is described by a model descriptor (PHOLD / MachRep2 / MachRep1) instead of a closure.
 Everything executes on the GPU through libtwb200.so (include/twb200.h); there is no CPU path here.
 """
 import ctypes as C
@@ -120,6 +120,19 @@ class MachRep2:
         p.machrep.mean_up_time = self.meanUpTime; p.machrep.mean_repair_time = self.meanRepairTime
         p.machrep.delta = self.delta; p.machrep.seed1 = self.seeds[0]; p.machrep.seed2 = self.seeds[1]
         p.machrep.seed_stride = self.seed_stride
+
+
+@dataclass
+class MachRep1(MachRep2):
+    """tests/MachRep1.hs replicated `n_replicas` times: two machines, two repair persons (LP 3r master, 3r+1/3r+2 slaves).
+
+    The second model of the reference's tests compiled through the handler table (csrc/engine.cu kModels); its slaves
+    report the up time with `sendMessage` (receive time = send time, no lookahead).  `delta` is unused."""
+    delta: float = 0.0
+
+    def fill(self, p):
+        super().fill(p)
+        p.model = ffi.TW_MODEL_MACHREP1
 
 
 @dataclass

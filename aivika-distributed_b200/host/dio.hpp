@@ -61,6 +61,13 @@ struct MachRep2 {          // tests/MachRep2DistributedReproducible.hs, replicat
         p.model = TW_MODEL_MACHREP2; p.n_lps = 3 * n_replicas; p.machrep = tw_machrep_params{meanUpTime, meanRepairTime, delta, seed1, seed2, seed_stride};
     }
 };
+struct MachRep1 {          // tests/MachRep1.hs (two repair persons), replicated; third model of the handler table
+    uint32_t n_replicas = 1; double meanUpTime = 1.0, meanRepairTime = 0.5; int64_t seed1 = 456, seed2 = 789, seed_stride = 1000;
+    void fill(tw_params &p) const
+    {
+        p.model = TW_MODEL_MACHREP1; p.n_lps = 3 * n_replicas; p.machrep = tw_machrep_params{meanUpTime, meanRepairTime, 0.0, seed1, seed2, seed_stride};
+    }
+};
 
 struct LogicalProcessState {
     uint32_t lpStateId; double lpStateLocalTime, lpStateEventQueueTime; uint32_t lpStateEventQueueSize, lpStateLogSize,

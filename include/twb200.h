@@ -43,7 +43,7 @@ enum {
     TW_ERR_NOT_SUPPORTED      = 12
 };
 
-enum { TW_MODEL_PHOLD = 1, TW_MODEL_MACHREP2 = 2 };
+enum { TW_MODEL_PHOLD = 1, TW_MODEL_MACHREP2 = 2, TW_MODEL_MACHREP1 = 3 };
 
 /* MachRep2 message kinds == the message data types of tests/MachRep2DistributedReproducible.hs:88-104 */
 enum {
@@ -53,6 +53,9 @@ enum {
     TW_MR_TOTAL_UP_TIME_CHANGE_RESP = 7, TW_MR_NREP_CHANGE_RESP = 8, TW_MR_NIMMED_REP_CHANGE_RESP = 9,
     TW_MR_REPAIR_PERSON_COUNT_RESP = 10, TW_MR_REQUEST_REPAIR_PERSON_RESP = 11, TW_MR_RELEASE_REPAIR_PERSON_RESP = 12
 };
+
+/* MachRep1 event kinds (tests/MachRep1.hs:52-72): the machine process as self-scheduled events + TotalUpTimeChange (:46-50) */
+enum { TW_M1_START = 0, TW_M1_UP_END = 1, TW_M1_REPAIR_END = 2, TW_M1_TOTAL_UP_TIME_CHANGE = 3 };
 
 /*
  * One timestamped message at the boundary (48 bytes).  Replaces `Message`
@@ -95,7 +98,7 @@ typedef struct tw_machrep_params {
  */
 typedef struct tw_params {
     uint32_t model;               /* TW_MODEL_* */
-    uint32_t n_lps;               /* global LP count (MachRep2: 3 * replicas) */
+    uint32_t n_lps;               /* global LP count (MachRep1/MachRep2: 3 * replicas) */
     uint32_t rank, world;         /* this partition / number of partitions (GPUs); LP i lives on i / ceil(n_lps/world) */
     int32_t  device;              /* CUDA device ordinal, -1 = current */
     uint32_t queue_capacity;      /* per-LP slots (power of two); ~ dioUndoableLogSizeThreshold / dioOutputMessageQueueSizeThreshold */
@@ -145,7 +148,8 @@ typedef struct tw_lp_state {
     uint64_t trace_hash;
 } tw_lp_state;
 
-/* Per-replica MachRep2 result: the pair returned by masterModel (:214-229). */
+/* Per-replica MachRep2 result: the pair returned by masterModel (:214-229).  MachRep1 (tests/MachRep1.hs:88-91) fills
+ * total_up_time, up_time_prop and n_rep (= TotalUpTimeChange messages received); the other fields are 0. */
 typedef struct tw_machrep_result {
     double  total_up_time;
     int64_t n_rep;
@@ -179,7 +183,7 @@ int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out);
 
 /* Per-LP committed-event counts and trace hashes for the LPs of this partition (n = local LP count). */
 int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *trace_hash, size_t n);
-/* MachRep2: results of the replicas whose master lives on this partition. */
+/* MachRep1/MachRep2: results of the replicas whose master lives on this partition. */
 int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n_replicas);
 
 /*

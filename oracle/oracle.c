@@ -11,6 +11,8 @@
  * model families of BASELINE.json:
  *   - the machine-repair model of tests/MachRep2DistributedReproducible.hs:125-229
  *     (slaveModel / masterModel, constants :61-74), replicated R times;
+ *   - the machine-repair model of tests/MachRep1.hs:52-93 (two repair persons, no contention; the `machine`
+ *     process as three self-scheduled events), replicated R times;
  *   - PHOLD (not in the reference; defined in SURVEY.md App. C / DESIGN.md) written
  *     against the reference's message API semantics (Optimistic/Message.hs:48-69:
  *     send time = current time, receive time chosen by the sender).
@@ -363,6 +365,70 @@ int oracle_machrep_run(const or_machrep_params *p, uint32_t r0, uint32_t r1, or_
     if (trace_len) *trace_len = 0;
     for (uint32_t r = r0; r < r1; ++r) {
         int rc = machrep_one(p, r, &res[r - r0], &h, trace, trace_cap, trace_len);
+        if (rc) { free(h.a); return rc; }
+    }
+    free(h.a);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ MachRep1 (tests/MachRep1.hs) */
+
+enum { M1_START = 0, M1_UP_END = 1, M1_REPAIR_END = 2, M1_TOTAL_UP_TIME_CHANGE = 3 };
+
+static int machrep1_one(const or_machrep_params *p, uint32_t r, or_machrep_result *res, or_heap *h)
+{
+    uint32_t base = 3 * r;
+    double total_up_time = 0.0; int64_t n_msgs = 0;          /* masterModel :75-93 */
+    or_stdgen gen[2];
+    uint64_t send_ctr[3] = {0, 0, 0}, n_exec[3] = {0, 0, 0}, hash[3];
+    gen[0] = or_mkstdgen(p->seed1 + (int64_t)r * p->seed_stride);
+    gen[1] = or_mkstdgen(p->seed2 + (int64_t)r * p->seed_stride);
+    for (int k = 0; k < 3; ++k) hash[k] = or_fin(or_lpkey(0, base + k) + 1ULL);
+    h->n = 0;
+    for (uint32_t me = 1; me <= 2; ++me) {                   /* runProcessInStartTime machine :68 */
+        or_event e; e.recv_ts = 0.0; e.send_ts = 0.0; e.ctr = send_ctr[me]++; e.src = base + me; e.dst = base + me;
+        e.type = M1_START; e.pad = 0; e.value = 0.0;
+        if (heap_push(h, &e)) return -1;
+    }
+    while (h->n > 0 && h->a[0].recv_ts <= p->stop_time) {
+        or_event e; heap_pop(h, &e);
+        uint32_t me = e.dst - base;
+        double t = e.recv_ts;
+        hash[me] = or_trace(hash[me], t, e.src, e.ctr);
+        if (e.type != M1_START) n_exec[me]++;
+        or_event o; o.send_ts = t; o.src = base + me; o.pad = 0;
+        switch (e.type) {
+        case M1_START:
+        case M1_REPAIR_END: {                                /* :55-58 upTime <- randomExponential meanUpTime; holdProcess upTime */
+            double up = or_expo(or_stdrandom_double(&gen[me - 1]), p->mean_up_time);
+            o.recv_ts = t + up; o.ctr = send_ctr[me]++; o.dst = base + me; o.type = M1_UP_END; o.value = up;
+            if (heap_push(h, &o)) return -1;
+            break; }
+        case M1_UP_END: {                                    /* :60-66 sendMessage masterId (TotalUpTimeChange upTime); repair */
+            o.recv_ts = t; o.ctr = send_ctr[me]++; o.dst = base; o.type = M1_TOTAL_UP_TIME_CHANGE; o.value = e.value;
+            if (heap_push(h, &o)) return -1;
+            double rt = or_expo(or_stdrandom_double(&gen[me - 1]), p->mean_repair_time);
+            o.recv_ts = t + rt; o.ctr = send_ctr[me]++; o.dst = base + me; o.type = M1_REPAIR_END; o.value = 0.0;
+            if (heap_push(h, &o)) return -1;
+            break; }
+        case M1_TOTAL_UP_TIME_CHANGE:                        /* :84-86 modifyRef totalUpTime (+ x) */
+            if (me == 0) { total_up_time += e.value; n_msgs++; }
+            break;
+        default: break;
+        }
+    }
+    res->total_up_time = total_up_time; res->n_rep = n_msgs; res->n_immed_rep = 0;
+    res->up_time_prop = total_up_time / (2.0 * p->stop_time);      /* :88-91 with n = 2 */
+    res->immed_prop = 0.0;
+    for (int k = 0; k < 3; ++k) { res->n_exec[k] = n_exec[k]; res->hash[k] = hash[k]; }
+    return 0;
+}
+
+int oracle_machrep1_run(const or_machrep_params *p, uint32_t r0, uint32_t r1, or_machrep_result *res)
+{
+    or_heap h = {0, 0, 0};
+    for (uint32_t r = r0; r < r1; ++r) {
+        int rc = machrep1_one(p, r, &res[r - r0], &h);
         if (rc) { free(h.a); return rc; }
     }
     free(h.a);

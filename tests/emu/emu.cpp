@@ -34,7 +34,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     const uint32_t cap = p->queue_capacity ? p->queue_capacity : 128;
     std::vector<Part<M>> parts(W);
     uint32_t n_per = (p->n_lps + W - 1) / W;
-    if (std::is_same<M, MachRepModel>::value && W > 1) n_per = ((n_per + 2) / 3) * 3;
+    if (M::kGroup > 1 && W > 1) n_per = ((n_per + M::kGroup - 1) / M::kGroup) * M::kGroup;
     for (uint32_t r = 0; r < W; ++r) {
         Part<M> &P = parts[r]; Dev<M> &d = P.d;
         memset(&d, 0, sizeof d);
@@ -61,8 +61,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     // initial events through the same routing function the k_route kernel uses
     std::vector<tw_event> init((size_t)p->n_lps * (p->model == TW_MODEL_PHOLD ? p->phold.population : 1) + 8);
     size_t n_init = 0;
-    if (p->model == TW_MODEL_PHOLD) n_init = PholdModel::initial_events(*p, init.data(), init.size());
-    else n_init = MachRepModel::initial_events(*p, init.data(), init.size());
+    n_init = M::initial_events(*p, init.data(), init.size());
     uint32_t step = 0; double gvt = p->start_time;
     Acc acc; acc.init();
     for (uint32_t r = 0; r < W; ++r)
@@ -105,12 +104,10 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         }
     if (st) *st = S;
     if (mr) {
-        if constexpr (std::is_same<M, MachRepModel>::value) {
+        if constexpr (M::kGroup == 3) {
             for (uint32_t lp = 0; lp < p->n_lps; lp += 3) {
-                const uint32_t r = lp / n_per; const MachRepModel::State &s = parts[r].state[lp - parts[r].d.lp_base];
-                tw_machrep_result &o = mr[lp / 3];
-                o.total_up_time = s.total_up_time; o.n_rep = s.n_rep; o.n_immed_rep = s.n_immed;
-                o.up_time_prop = s.total_up_time / (2.0 * p->stop_time); o.immed_prop = (double)s.n_immed / (double)s.n_rep;
+                const uint32_t r = lp / n_per;
+                mr[lp / 3] = M::result(parts[r].state[lp - parts[r].d.lp_base], p->stop_time);
             }
         }
     }
@@ -139,5 +136,6 @@ extern "C" int emu_run(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_ex
 {
     if (p->model == TW_MODEL_PHOLD) return emu_run_t<PholdModel>(p, shuffle_seed, n_exec, hash, mr, st);
     if (p->model == TW_MODEL_MACHREP2) return emu_run_t<MachRepModel>(p, shuffle_seed, n_exec, hash, mr, st);
+    if (p->model == TW_MODEL_MACHREP1) return emu_run_t<MachRep1Model>(p, shuffle_seed, n_exec, hash, mr, st);
     return TW_ERR_INVALID_ARG;
 }

@@ -20,6 +20,14 @@ json.dump({"config": "tests/MachRep2DistributedReproducible.hs: seeds 456/789, s
            "n_exec": list(r.n_exec), "hash": [hex(x) for x in r.hash]},
           open(os.path.join(here, "machrep2_c1.json"), "w"), indent=1)
 
+r = H.oracle_machrep1(H.machrep1_params(1, 10000.0))[0]
+json.dump({"config": "tests/MachRep1.hs: two machines, two repair persons, means 1.0/0.5, stop 10000; StdGen seeds 456/789 "
+                     "(the reference draws from the run's default generator, which is not reproducible)",
+           "up_time_prop": r.up_time_prop.hex(), "up_time_prop_decimal": r.up_time_prop,
+           "total_up_time": r.total_up_time.hex(), "n_messages": r.n_rep,
+           "n_exec": list(r.n_exec), "hash": [hex(x) for x in r.hash]},
+          open(os.path.join(here, "machrep1.json"), "w"), indent=1)
+
 cases = []
 for params in (dict(n_lps=64, stop=5.0, remote_pct=10), dict(n_lps=1000, stop=3.0, remote_pct=50, seed=3),
                dict(n_lps=512, stop=4.0, remote_pct=50, n_hot=8, hot_pct=50, seed=11),

@@ -77,7 +77,8 @@ def oracle():
     global _oracle
     if _oracle is None:
         d = os.path.join(ROOT, "oracle")
-        if not os.path.exists(os.path.join(d, "liboracle.so")):
+        so = os.path.join(d, "liboracle.so")
+        if not os.path.exists(so) or any(os.path.getmtime(os.path.join(d, f)) > os.path.getmtime(so) for f in ("oracle.c", "oracle_math.h")):
             _make(d, "liboracle.so")
         L = C.CDLL(os.path.join(d, "liboracle.so"))
         L.oracle_log.restype = C.c_double; L.oracle_log.argtypes = [C.c_double]
@@ -91,6 +92,7 @@ def oracle():
         L.oracle_phold_initial_events.argtypes = [C.POINTER(or_phold_params), C.c_void_p]
         L.oracle_machrep_run.argtypes = [C.POINTER(or_machrep_params), C.c_uint32, C.c_uint32, C.c_void_p,
                                          C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.oracle_machrep1_run.argtypes = [C.POINTER(or_machrep_params), C.c_uint32, C.c_uint32, C.c_void_p]
         _oracle = L
     return _oracle
 
@@ -137,6 +139,26 @@ def machrep_params(n_replicas, stop=1000.0, horizon=-1.0, cap=64, batch=4, world
     p.machrep.mean_up_time = 1.0; p.machrep.mean_repair_time = 0.5; p.machrep.delta = 1e-6
     p.machrep.seed1 = seed1; p.machrep.seed2 = seed2; p.machrep.seed_stride = stride
     return p
+
+
+def machrep1_params(n_replicas, stop=1000.0, horizon=-1.0, cap=64, batch=4, world=1, rank=0, steps_per_launch=32,
+                    seed1=456, seed2=789, stride=1000):
+    """tests/MachRep1.hs replicated (constants :39-40); the StdGen seeds follow the reproducible MachRep2 variant."""
+    p = machrep_params(n_replicas, stop, horizon, cap, batch, world, rank, steps_per_launch, seed1, seed2, stride)
+    p.model = ffi.TW_MODEL_MACHREP1
+    p.machrep.delta = 0.0
+    return p
+
+
+def oracle_machrep1(p, r0=0, r1=None):
+    n_rep = p.n_lps // 3
+    r1 = n_rep if r1 is None else r1
+    op = or_machrep_params(n_rep, 0, p.machrep.mean_up_time, p.machrep.mean_repair_time, p.machrep.delta,
+                           p.stop_time, p.machrep.seed1, p.machrep.seed2, p.machrep.seed_stride)
+    res = (or_machrep_result * (r1 - r0))()
+    rc = oracle().oracle_machrep1_run(C.byref(op), r0, r1, res)
+    assert rc == 0, rc
+    return res
 
 
 def oracle_phold(p):

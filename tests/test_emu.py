@@ -95,6 +95,28 @@ def test_machrep2_partitioned_keeps_replicas_whole(H):
     check_machrep(H, H.machrep_params(7, 100.0, horizon=5.0, world=3), seeds=(1,))
 
 
+def check_machrep1(H, p, seeds=(0, 5)):
+    res = H.oracle_machrep1(p)
+    for sd in seeds:
+        rc, n_exec, h, mr, stats = H.emu_run(p, sd)
+        assert rc == 0
+        for r in range(p.n_lps // 3):
+            o, m = res[r], mr[r]
+            assert (o.total_up_time, o.n_rep) == (m.total_up_time, m.n_rep) and o.up_time_prop == m.up_time_prop
+            assert [o.n_exec[k] for k in range(3)] == [int(n_exec[3 * r + k]) for k in range(3)]
+            assert [o.hash[k] for k in range(3)] == [int(h[3 * r + k]) for k in range(3)]
+    return stats
+
+
+@pytest.mark.parametrize("horizon,batch,world", [(-1.0, 4, 1), (5.0, 8, 1), (0.5, 2, 3), (0.0, 4, 1)])
+def test_machrep1_third_model_through_the_handler_table(H, horizon, batch, world):
+    """tests/MachRep1.hs: the slaves never receive anything and run ahead, the master gets zero-lookahead messages
+    (sendMessage: receive time = send time) from two senders and must commit them in time order."""
+    st_ = check_machrep1(H, H.machrep1_params(5, 300.0, horizon=horizon, batch=batch, world=world, cap=512), seeds=(3,))
+    if horizon != 0.0:
+        assert st_.rolled_back > 0
+
+
 @settings(max_examples=25, deadline=None)
 @given(n=st.integers(2, 200), pop=st.integers(1, 6), rp=st.integers(0, 100), hor=st.sampled_from([0.05, 0.3, 1.5, -1.0]),
        batch=st.sampled_from([1, 2, 3, 4, 6, 7, 16, 64]), seed=st.integers(0, 2 ** 32), world=st.sampled_from([1, 2, 4]), shuffle=st.integers(0, 99))

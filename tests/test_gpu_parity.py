@@ -123,6 +123,36 @@ def test_machrep2_replicas(H, horizon):
         assert [int(h[3 * r + k]) for k in range(3)] == [o.hash[k] for k in range(3)]
 
 
+@pytest.mark.parametrize("horizon", [None, 5.0, 0.0])
+def test_machrep1_replicas(H, horizon):
+    """tests/MachRep1.hs through the handler table (third compiled model): per-replica result, per-LP counts and trace
+    hashes equal the sequential oracle's; replica 0 equals the golden fixture."""
+    import json, os
+    d = D()
+    n = 64
+    dio, sim = d.runDIO(d.MachRep1(n), d.DIOParams(dioTimeHorizon=horizon, queueCapacity=512, maxEventsPerStep=8, stepsPerLaunch=32),
+                        d.timeServer(3 * n), d.Specs(0.0, 400.0))
+    st, n_exec, h, res = sim()
+    dio.close()
+    ores = H.oracle_machrep1(H.machrep1_params(n, 400.0))
+    for r in range(n):
+        o = ores[r]
+        assert res[r]["total_up_time"] == o.total_up_time and res[r]["n_rep"] == o.n_rep
+        assert res[r]["up_time_prop"] == o.up_time_prop
+        assert [int(n_exec[3 * r + k]) for k in range(3)] == [o.n_exec[k] for k in range(3)]
+        assert [int(h[3 * r + k]) for k in range(3)] == [o.hash[k] for k in range(3)]
+    if horizon != 0.0:
+        assert st.rolled_back > 0
+    if horizon is None:
+        dio, sim = d.runDIO(d.MachRep1(1), d.DIOParams(queueCapacity=1024, maxEventsPerStep=16, stepsPerLaunch=32), d.timeServer(3),
+                            d.Specs(0.0, 10000.0))
+        st, n_exec, h, res = sim()
+        dio.close()
+        g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "machrep1.json")))
+        assert float(res[0]["up_time_prop"]).hex() == g["up_time_prop"] and [int(x) for x in n_exec] == g["n_exec"]
+        assert abs(res[0]["up_time_prop"] - 0.66) < 0.01          # "Should get value of about 0.66"
+
+
 def test_full_size_c3_invariants(H):
     """PHOLD 64K LPs / 10 % remote (BASELINE configs[2]) at a shortened stop time the oracle finishes in seconds,
     then at full horizon sweep: identical committed trace for every window, zero rollbacks when conservative."""
