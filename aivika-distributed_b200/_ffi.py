@@ -27,6 +27,7 @@ ERROR_NAMES = {
 EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
     "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range",
+    "tw_attach_time_server", "tw_local_time", "tw_global_time_message",
     "tw_nccl_unique_id", "tw_last_error", "tw_strerror", "tw_version", "tw_kernel_launch_count",
 ]
 
@@ -111,6 +112,9 @@ def load(path=None):
     lib.tw_read_lp_stats.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t]; lib.tw_read_lp_stats.restype = C.c_int
     lib.tw_read_machrep.argtypes = [H, C.c_void_p, C.c_size_t]; lib.tw_read_machrep.restype = C.c_int
     lib.tw_set_monitor.argtypes = [H, MONITOR_FN, C.c_void_p]; lib.tw_set_monitor.restype = C.c_int
+    lib.tw_attach_time_server.argtypes = [H, C.c_int]; lib.tw_attach_time_server.restype = C.c_int
+    lib.tw_local_time.argtypes = [H, C.POINTER(C.c_double)]; lib.tw_local_time.restype = C.c_int
+    lib.tw_global_time_message.argtypes = [H, C.c_double, C.POINTER(C.c_int)]; lib.tw_global_time_message.restype = C.c_int
     lib.tw_partition.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; lib.tw_partition.restype = C.c_int
     lib.tw_model_initial_events.argtypes = [C.POINTER(tw_params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.tw_model_initial_events.restype = C.c_int

@@ -92,7 +92,7 @@ __device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer
     const unsigned long long m = warp_min_u64(ordered_bits(v));
     if (r == 0) {
         if (bad) { if (atomicCAS(&ctl->error, 0u, bad) == 0u) ctl->err_lp = 0xFFFFFFFFu; }
-        else ctl->gvt = from_ordered(m);
+        else { const double g = from_ordered(m), cap = *(volatile double *)&ctl->gvt_cap; ctl->gvt = g < cap ? g : cap; }
     }
 }
 
@@ -141,7 +141,7 @@ __device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t 
             const unsigned long long em = *(volatile unsigned long long *)&ctl->emit_min;
             g = from_ordered(pm < em ? pm : em);
             ctl->gvt_local = g;
-            if (world == 1) ctl->gvt = g;            // otherwise the cross-GPU minimum follows
+            if (world == 1) { const double cap = *(volatile double *)&ctl->gvt_cap; ctl->gvt = g < cap ? g : cap; }   // otherwise the cross-GPU minimum follows
             ctl->pend_min = ordered_bits(pos_inf());
             ctl->emit_min = ordered_bits(pos_inf());
             ctl->step = step + 1; ctl->c_steps += 1;
@@ -211,6 +211,14 @@ __global__ void k_gvt_exchange(Ctl *ctl, GvtSlot *const *peer_slots_dev, uint32_
 }
 
 // after k_route: gvt = min(gvt, injected minimum)   (single thread)
+// GlobalTimeMessage from an external Time Server (single thread): the bound moves, GVT follows up to the local minimum
+__global__ void k_set_gvt_cap(Ctl *ctl, double cap, uint32_t world)
+{
+    ctl->gvt_cap = cap;
+    if (world == 1) ctl->gvt = ctl->gvt_local < cap ? ctl->gvt_local : cap;
+    else if (cap < ctl->gvt) ctl->gvt = cap;         // multi-GPU: the next mailbox round raises it again
+}
+
 __global__ void k_fold_inject(Ctl *ctl)
 {
     const double m = from_ordered(ctl->emit_min);
@@ -220,7 +228,7 @@ __global__ void k_fold_inject(Ctl *ctl)
 }
 
 template <class M>
-__global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_time)
+__global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_time, double cap0)
 {
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
     if (l == 0) {
@@ -229,6 +237,7 @@ __global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_ti
         Ctl c; memset(&c, 0, sizeof c);
         c.step = next_step;
         c.gvt = start_time; c.gvt_local = start_time;
+        c.gvt_cap = cap0;
         c.pend_min = ordered_bits(pos_inf()); c.emit_min = ordered_bits(pos_inf());
         *d.ctl = c;
     }
@@ -317,6 +326,9 @@ struct EngineBase {
     virtual int read_lp_stats(uint64_t *n_exec, uint64_t *hash, size_t n) = 0;
     virtual int read_machrep(tw_machrep_result *out, size_t n) = 0;
     virtual void partition(uint32_t *base, uint32_t *n) const = 0;
+    virtual int local_time(double *t) = 0;
+    virtual int global_time_message(double t, int *accepted) = 0;
+    virtual int attach_time_server(int on) = 0;
     tw_monitor_fn monitor = nullptr; void *monitor_user = nullptr;
 };
 
@@ -372,6 +384,7 @@ struct Engine : EngineBase {
     std::vector<void *> peer_ptrs;        // opened IPC mappings
     uint64_t launches = 0;
     int grid = 0, step_grid = 0;
+    bool external_time = false;           // GVT bounded by an external Time Server (tw_attach_time_server)
     void *meta = nullptr; size_t meta_bytes = 0, l2_window_bytes = 0, l2_persist_bytes = 0;
     GvtSlot *d_slots = nullptr; GvtSlot **d_peer_slots = nullptr;      // my GVT mailbox; device copy of the peer table
 
@@ -520,7 +533,8 @@ struct Engine : EngineBase {
 
     int reset() override
     {
-        k_init<M><<<grid, kBlock, 0, stream>>>(d, P.start_time); count(1);
+        // an engine attached to an external Time Server starts with GVT pinned to the start time
+        k_init<M><<<grid, kBlock, 0, stream>>>(d, P.start_time, external_time ? P.start_time : (double)INFINITY); count(1);
         TW_CUDA(cudaGetLastError());
         if (d_slots) TW_CUDA(cudaMemsetAsync(d_slots, 0xFE, 2 * kMaxWorld * sizeof(GvtSlot), stream));   // tags = kSlotEmpty
         TW_CUDA(cudaStreamSynchronize(stream));
@@ -620,6 +634,7 @@ struct Engine : EngineBase {
                 }
                 if ((result = check_device_error(last)) != TW_OK) break;
                 if (!(last.gvt <= until)) { finished = true; break; }
+                if (external_time && !(last.gvt < last.gvt_cap)) break;       // waiting for the next GlobalTimeMessage
                 if (last.gvt == last_gvt) { if (++stall > 4096) { err = code_name(TW_ERR_DEADLOCK); result = TW_ERR_DEADLOCK; break; } }
                 else { stall = 0; last_gvt = last.gvt; }
             }
@@ -696,6 +711,32 @@ struct Engine : EngineBase {
     int read_machrep(tw_machrep_result *out, size_t n) override;
 
     void partition(uint32_t *base, uint32_t *n) const override { if (base) *base = d.lp_base; if (n) *n = d.n_local; }
+
+    // ---- the Time Server role across partitions
+    // getLocalTime / LocalTimeMessage (Internal/Event.hs:425-436, 496-514): this partition's minimum over unprocessed and
+    // in-flight messages, whatever the bound says.
+    int local_time(double *t) override
+    {
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        *t = h_ctl[0].gvt_local;
+        return TW_OK;
+    }
+    // GlobalTimeMessage / updateGlobalTime (Internal/Event.hs:437-449, 528-540): a global time above the local time is
+    // ignored, otherwise it becomes the bound of GVT (fossil collection, commitment, termination).
+    int global_time_message(double t, int *accepted) override
+    {
+        if (!external_time) { err = "no external Time Server attached (tw_attach_time_server)"; return TW_ERR_INVALID_ARG; }
+        double lt = 0.0; int rc = local_time(&lt); if (rc) return rc;
+        const bool ok = !(t > lt) && !(t < h_ctl[0].gvt_cap);          // never backwards either
+        if (accepted) *accepted = ok ? 1 : 0;
+        if (!ok) return TW_OK;
+        k_set_gvt_cap<<<1, 1, 0, stream>>>(d.ctl, t, d.world); count(1);
+        TW_CUDA(cudaGetLastError());
+        TW_CUDA(cudaStreamSynchronize(stream));
+        return TW_OK;
+    }
+    int attach_time_server(int on) override { external_time = on != 0; return reset(); }
 
     ~Engine() override
     {
@@ -786,6 +827,9 @@ int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out) { return (e && 
 int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *hash, size_t n) { return (e && n_exec && hash) ? e->impl->read_lp_stats(n_exec, hash, n) : TW_ERR_INVALID_ARG; }
 int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n) { return (e && out) ? e->impl->read_machrep(out, n) : TW_ERR_INVALID_ARG; }
 int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user) { if (!e) return TW_ERR_INVALID_ARG; e->impl->monitor = fn; e->impl->monitor_user = user; return TW_OK; }
+int tw_attach_time_server(tw_engine *e, int on) { return e ? e->impl->attach_time_server(on) : TW_ERR_INVALID_ARG; }
+int tw_local_time(tw_engine *e, double *t) { return (e && t) ? e->impl->local_time(t) : TW_ERR_INVALID_ARG; }
+int tw_global_time_message(tw_engine *e, double t, int *accepted) { return e ? e->impl->global_time_message(t, accepted) : TW_ERR_INVALID_ARG; }
 int tw_partition(const tw_engine *e, uint32_t *base, uint32_t *n) { if (!e) return TW_ERR_INVALID_ARG; e->impl->partition(base, n); return TW_OK; }
 
 int tw_model_initial_events(const tw_params *p, tw_event *out, size_t cap, size_t *n)

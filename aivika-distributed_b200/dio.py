@@ -71,15 +71,40 @@ defaultTimeServerParams = TimeServerParams()
 
 @dataclass
 class TimeServer:
-    """The Time Server role (Internal/TimeServer.hs:485): quorum of LPs + the global virtual time."""
+    """The Time Server role (Internal/TimeServer.hs:485): quorum of LPs + the global virtual time.
+
+    With a single device partition the role collapses into the in-kernel reduction (`globalTime`).  With several
+    registered logical processes -- device partitions (DIO objects after `attachTimeServer`) or CPU processes, anything
+    with `localTime()` and `globalTimeMessage(t)` -- `computeGlobalTime` is one round of the reference's protocol:
+    ComputeLocalTimeMessage to everybody, LocalTimeMessage back, minimum, GlobalTimeMessage to everybody
+    (computeTimeServerGlobalTime / timeServerGlobalTime / provideTimeServerGlobalTime, Internal/TimeServer.hs:369-421)."""
     quorum: int
     params: TimeServerParams = field(default_factory=TimeServerParams)
     _dio: Optional["DIO"] = None
+    _processes: list = field(default_factory=list)
+    _global_time: Optional[float] = None
 
     def globalTime(self):
+        if self._processes:
+            return self._global_time
         if self._dio is None:
             return None
         return self._dio.globalTime()
+
+    def register(self, lp):
+        """RegisterLogicalProcessMessage (Internal/TimeServer.hs:196-222)."""
+        self._processes.append(lp)
+
+    def computeGlobalTime(self):
+        """One GVT round; returns the global time, or None while the quorum is not met (:311-326)."""
+        if len(self._processes) < self.quorum:
+            return None
+        local = [lp.localTime() for lp in self._processes]
+        t0 = min(local)
+        self._global_time = t0
+        for lp in self._processes:
+            lp.globalTimeMessage(t0)
+        return t0
 
 
 def timeServer(n, params=defaultTimeServerParams):
@@ -243,6 +268,23 @@ class DIO:
         g = C.c_double()
         self._check(self.lib.tw_gvt(self.h, C.byref(g)))
         return g.value
+
+    # -- the LP side of the Time Server protocol (Internal/TimeServer.hs; tw_attach_time_server & co.)
+    def attachTimeServer(self, on=True):
+        """registerDIO: GVT is bounded by the Time Server's GlobalTimeMessage from now on (resets the run)."""
+        self._check(self.lib.tw_attach_time_server(self.h, 1 if on else 0))
+
+    def localTime(self):
+        """The answer to ComputeLocalTimeMessage: the partition's local minimum time (LocalTimeMessage)."""
+        t = C.c_double()
+        self._check(self.lib.tw_local_time(self.h, C.byref(t)))
+        return t.value
+
+    def globalTimeMessage(self, t):
+        """GlobalTimeMessage t -> updateGlobalTime; returns False when the value was ignored (above the local time)."""
+        ok = C.c_int()
+        self._check(self.lib.tw_global_time_message(self.h, t, C.byref(ok)))
+        return bool(ok.value)
 
     def logicalProcessState(self, lp):
         s = ffi.tw_lp_state()

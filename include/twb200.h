@@ -201,6 +201,21 @@ typedef struct tw_monitor_state {
 typedef void (*tw_monitor_fn)(const tw_monitor_state *state, void *user);
 int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user);
 
+/*
+ * The Time Server role across partitions: the LP side of the protocol of Internal/TimeServer.hs, so
+ * that a device partition can sit under an external Time Server next to other partitions or CPU logical processes.
+ *   tw_attach_time_server(e, 1)  registerDIO / RegisterLogicalProcessMessage (Internal/DIO.hs:267-283): from now on GVT
+ *                                is bounded by the last accepted GlobalTimeMessage (initially the start time); resets the run
+ *   tw_local_time                the answer to ComputeLocalTimeMessage: LocalTimeMessage pid t (Internal/Event.hs:425-436,
+ *                                getLocalTime :496-514)
+ *   tw_global_time_message       GlobalTimeMessage t -> updateGlobalTime (Internal/Event.hs:437-449, 528-540): a value above
+ *                                the local time is ignored (*accepted = 0), otherwise fossil collection and termination use it
+ * tw_run on an attached engine returns when GVT has passed until_time or sits at the bound (stats->gvt tells which).
+ */
+int tw_attach_time_server(tw_engine *e, int on);
+int tw_local_time(tw_engine *e, double *local_time);
+int tw_global_time_message(tw_engine *e, double global_time, int *accepted);
+
 /* Partition geometry: first global LP id and LP count owned by this rank. */
 int tw_partition(const tw_engine *e, uint32_t *lp_base, uint32_t *n_local);
 

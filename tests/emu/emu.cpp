@@ -27,7 +27,7 @@ static uint64_t rng_next(uint64_t &s) { s += kGolden; return mix_fin(s); }
 
 template <class M>
 static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,
-                     tw_machrep_result *mr, tw_run_stats *st)
+                     tw_machrep_result *mr, tw_run_stats *st, uint32_t gvt_every = 1)
 {
     const uint32_t W = p->world ? p->world : 1;
     if (W > (uint32_t)kMaxWorld) return TW_ERR_INVALID_ARG;
@@ -74,6 +74,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     uint64_t rs = shuffle_seed;
     tw_run_stats S; memset(&S, 0, sizeof S);
     uint64_t stall = 0;
+    double local_min = gvt;                 // what the partition would report as its local time; `gvt` may lag behind it
     while (gvt <= p->stop_time) {
         double wend = p->stop_time;
         if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
@@ -82,9 +83,12 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step); }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
         const double g = std::min(acc.pend_min, acc.emit_min);
-        if (g < gvt) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", gvt, g, step); return 100; }
-        if (g == gvt) { if (++stall > 100000) return TW_ERR_DEADLOCK; } else stall = 0;
-        gvt = g; step++;
+        if (g < local_min) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", local_min, g, step); return 100; }
+        if (g == local_min) { if (++stall > 100000) return TW_ERR_DEADLOCK; } else stall = 0;
+        local_min = g; step++;
+        // an external Time Server hands out the global time only now and then (tw_global_time_message): until then the
+        // engine keeps working with the old, lower bound
+        if (step % gvt_every == 0 || !(g <= p->stop_time)) gvt = g;
         S.steps++; S.executed += acc.exec; S.rolled_back += acc.rb_events; S.rollbacks += acc.rollbacks; S.stragglers += acc.strag;
         S.anti_sent += acc.anti; S.annihilated += acc.annih; S.retries += acc.retry; S.sent_local += acc.sent_local; S.sent_remote += acc.sent_remote;
     }
@@ -129,6 +133,17 @@ extern "C" int emu_phold_reverse_roundtrip(uint64_t seed, int n)
         if (mix_fin_inv(mix_fin(a.hash)) != a.hash) ++bad;
     }
     return bad;
+}
+
+// the same run with GVT refreshed only every `gvt_every` super-steps (an external Time Server's bound)
+extern "C" int emu_run_lagged(const tw_params *p, uint64_t shuffle_seed, uint32_t gvt_every, uint64_t *n_exec, uint64_t *hash,
+                              tw_machrep_result *mr, tw_run_stats *st)
+{
+    if (gvt_every == 0) gvt_every = 1;
+    if (p->model == TW_MODEL_PHOLD) return emu_run_t<PholdModel>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every);
+    if (p->model == TW_MODEL_MACHREP2) return emu_run_t<MachRepModel>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every);
+    if (p->model == TW_MODEL_MACHREP1) return emu_run_t<MachRep1Model>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every);
+    return TW_ERR_INVALID_ARG;
 }
 
 extern "C" int emu_run(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,

@@ -114,6 +114,9 @@ def emu():
         L.emu_run.argtypes = [C.POINTER(ffi.tw_params), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.POINTER(ffi.tw_run_stats)]
         L.emu_run.restype = C.c_int
+        L.emu_run_lagged.argtypes = [C.POINTER(ffi.tw_params), C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(ffi.tw_run_stats)]
+        L.emu_run_lagged.restype = C.c_int
         _emu = L
     return _emu
 
@@ -184,12 +187,15 @@ def oracle_machrep(p, r0=0, r1=None):
     return res
 
 
-def emu_run(p, shuffle_seed=1):
+def emu_run(p, shuffle_seed=1, gvt_every=1):
     import numpy as np
     n_exec = np.zeros(p.n_lps, dtype=np.uint64); h = np.zeros(p.n_lps, dtype=np.uint64)
     mr = (ffi.tw_machrep_result * max(1, p.n_lps // 3))()
     st = ffi.tw_run_stats()
-    rc = emu().emu_run(C.byref(p), shuffle_seed, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
+    if gvt_every == 1:
+        rc = emu().emu_run(C.byref(p), shuffle_seed, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
+    else:
+        rc = emu().emu_run_lagged(C.byref(p), shuffle_seed, gvt_every, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
     return rc, n_exec, h, mr, st
 
 

@@ -137,3 +137,17 @@ def test_phold_equal_timestamps_exercise_full_key_ordering(H):
 def test_phold_reverse_computation_is_the_exact_inverse(H):
     """PHOLD is rolled back by reverse computation (no saved states): reverse(advance(s, e), e) == s for random words."""
     assert H.emu().emu_phold_reverse_roundtrip(12345, 200000) == 0
+
+
+@pytest.mark.parametrize("every", [2, 7, 40])
+def test_lagging_global_time_of_an_external_time_server(H, every):
+    """under an external Time Server the engine only learns the global time now and then
+    (GlobalTimeMessage); with any lower bound of the true GVT the committed trace must stay the sequential one."""
+    p = H.phold_params(400, 6.0, remote_pct=40, horizon=0.5, batch=8, cap=1024, proc_limit=256)
+    n_exec, h, s = H.oracle_phold(p)
+    rc, e_exec, e_hash, _, st_ = H.emu_run(p, 3, gvt_every=every)
+    assert rc == 0 and (e_exec == n_exec).all() and (e_hash == h).all() and st_.committed == s.committed
+    pm = H.machrep_params(4, 120.0, horizon=5.0, batch=4, cap=1024)
+    res = H.oracle_machrep(pm)
+    rc, n_exec, h, mr, _ = H.emu_run(pm, 2, gvt_every=every)
+    assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop for r in range(4))

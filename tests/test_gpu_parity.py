@@ -153,6 +153,50 @@ def test_machrep1_replicas(H, horizon):
         assert abs(res[0]["up_time_prop"] - 0.66) < 0.01          # "Should get value of about 0.66"
 
 
+def test_two_partitions_under_one_time_server(H):
+    """two device partitions and a CPU process registered with one host-side Time Server.  GVT of every
+    partition is bounded by the server's GlobalTimeMessage (minimum over all local times), a value above the local time
+    is ignored, and the committed traces equal the stand-alone runs (= the oracle)."""
+    d = D()
+
+    class CpuProcess:                      # a logical process that only advances its clock
+        def __init__(self): self.t = 0.0; self.seen = []
+        def localTime(self): return self.t
+        def globalTimeMessage(self, t): self.seen.append(t); return True
+
+    pa = H.phold_params(3000, 6.0, remote_pct=40, horizon=0.5, batch=8, seed=11, cap=256)
+    pb = H.phold_params(1000, 6.0, remote_pct=20, horizon=1.0, batch=4, seed=12, cap=256)
+    mk = lambda p: d.DIO(d.PHOLD(p.n_lps, p.phold.population, p.phold.remote_pct, p.phold.lookahead, p.phold.mean, p.phold.seed),
+                         d.DIOParams(dioTimeHorizon=p.time_horizon, queueCapacity=p.queue_capacity,
+                                     maxEventsPerStep=p.max_events_per_step, stepsPerLaunch=4), d.Specs(0.0, p.stop_time))
+    a, b, cpu = mk(pa), mk(pb), CpuProcess()
+    ts = d.timeServer(3)
+    for lp in (a, b):
+        lp.attachTimeServer()
+        lp.enqueueMessages(lp.initialEvents())
+        ts.register(lp)
+    assert ts.computeGlobalTime() is None          # quorum of 3 not met yet
+    ts.register(cpu)
+    assert a.globalTimeMessage(1e9) is False        # above the local time: ignored (Internal/Event.hs:533-536)
+    rounds, done = 0, False
+    while not done:
+        sa, sb = a.runEventInStopTime(), b.runEventInStopTime()
+        g = ts.globalTime()
+        assert g is None or (sa.gvt <= g and sb.gvt <= g) or (sa.gvt > 6.0 and sb.gvt > 6.0)
+        cpu.t = min(cpu.t + 0.37, 1e30) if cpu.t < 7.0 else 1e30      # the CPU process lags, then finishes
+        g = ts.computeGlobalTime()
+        assert g == min(a.localTime(), b.localTime(), cpu.t)
+        rounds += 1
+        done = sa.gvt > 6.0 and sb.gvt > 6.0
+        assert rounds < 5000
+    assert rounds > 10 and cpu.seen == sorted(cpu.seen)          # the global time never decreases
+    for lp, p in ((a, pa), (b, pb)):
+        n_exec, h = lp.lpStats()
+        o_exec, o_hash, _ = H.oracle_phold(p)
+        assert (n_exec == o_exec).all() and (h == o_hash).all()
+        lp.close()
+
+
 def test_full_size_c3_invariants(H):
     """PHOLD 64K LPs / 10 % remote (BASELINE configs[2]) at a shortened stop time the oracle finishes in seconds,
     then at full horizon sweep: identical committed trace for every window, zero rollbacks when conservative."""
