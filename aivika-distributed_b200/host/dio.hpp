@@ -136,6 +136,10 @@ class DIO {
         return st;
     }
     double globalTime() const { double g = 0; check(tw_gvt(h_, &g)); return g; }
+    // the LP side of the Time Server protocol (Internal/TimeServer.hs): registerDIO, LocalTimeMessage, GlobalTimeMessage
+    void attachTimeServer(bool on = true) { check(tw_attach_time_server(h_, on ? 1 : 0)); }
+    double localTime() const { double t = 0; check(tw_local_time(h_, &t)); return t; }
+    bool globalTimeMessage(double t) { int ok = 0; check(tw_global_time_message(h_, t, &ok)); return ok != 0; }
     LogicalProcessState logicalProcessState(uint32_t lp) const
     {
         tw_lp_state s{}; check(tw_lp_state_get(h_, lp, &s));

@@ -12,12 +12,15 @@
 -- @GlobalTimeMessage@ would carry, Internal/TimeServer.hs:384-403).
 --
 -- Arbitrary Haskell closures cannot run on the device, so a batch of homogeneous LPs is described by a
--- compiled model ('ModelPHOLD' / 'ModelMachRep2') instead of a @Simulation DIO a@ value.
+-- compiled model ('ModelPHOLD' / 'ModelMachRep2' / 'ModelMachRep1') instead of a @Simulation DIO a@ value.
+-- Under an external Time Server (Internal/TimeServer.hs) a batch behaves like one logical process:
+-- 'attachTimeServerB200', 'localTimeB200' (the @LocalTimeMessage@ payload) and 'globalTimeMessageB200'.
 -- All calls are @safe@ so the RTS keeps running other Haskell threads during 'twRun'.
 module Simulation.Aivika.Distributed.Optimistic.B200
        (B200Model(..), B200Specs(..), B200Params(..), defaultB200Params, RunStats(..), MachRepResult(..),
         B200Engine, runDIOBatch, newB200Engine, freeB200Engine, loadInitialMessages,
-        enqueueMessageB200, runEventInStopTimeB200, globalTimeB200, readMachRep2) where
+        enqueueMessageB200, runEventInStopTimeB200, globalTimeB200, readMachRep2,
+        attachTimeServerB200, localTimeB200, globalTimeMessageB200) where
 
 import Control.Exception (throwIO, ErrorCall(..), bracket)
 import Control.Monad (when)
@@ -36,6 +39,8 @@ data B200Model
                , pholdHot :: Word32, pholdHotPct :: Word32 }
   | ModelMachRep2 { mrReplicas :: Word32, mrMeanUpTime :: Double, mrMeanRepairTime :: Double
                   , mrDelta :: Double, mrSeed1 :: Int64, mrSeed2 :: Int64, mrSeedStride :: Int64 }
+  | ModelMachRep1 { m1Replicas :: Word32, m1MeanUpTime :: Double, m1MeanRepairTime :: Double
+                  , m1Seed1 :: Int64, m1Seed2 :: Int64, m1SeedStride :: Int64 }     -- tests/MachRep1.hs
 
 data B200Specs = B200Specs { spcStartTime :: Double, spcStopTime :: Double }
 
@@ -66,6 +71,9 @@ foreign import ccall safe "tw_run"     c_tw_run     :: Ptr () -> CDouble -> Ptr 
 foreign import ccall safe "tw_gvt"     c_tw_gvt     :: Ptr () -> Ptr CDouble -> IO CInt
 foreign import ccall safe "tw_read_machrep" c_tw_read_machrep :: Ptr () -> Ptr () -> CSize -> IO CInt
 foreign import ccall safe "tw_model_initial_events" c_tw_model_initial_events :: Ptr () -> Ptr () -> CSize -> Ptr CSize -> IO CInt
+foreign import ccall safe "tw_attach_time_server" c_tw_attach_time_server :: Ptr () -> CInt -> IO CInt
+foreign import ccall safe "tw_local_time" c_tw_local_time :: Ptr () -> Ptr CDouble -> IO CInt
+foreign import ccall safe "tw_global_time_message" c_tw_global_time_message :: Ptr () -> CDouble -> Ptr CInt -> IO CInt
 foreign import ccall unsafe "tw_last_error" c_tw_last_error :: Ptr () -> IO CString
 
 -- | Non-zero status becomes an 'error', like the invariants of the reference (e.g. Internal/Event.hs:374).
@@ -97,6 +105,10 @@ pokeParams p model B200Params{..} B200Specs{..} = do
       pokeByteOff p 0 (2 :: Word32); pokeByteOff p 4 (3 * mrReplicas)
       pokeByteOff p 112 mrMeanUpTime; pokeByteOff p 120 mrMeanRepairTime; pokeByteOff p 128 mrDelta
       pokeByteOff p 136 mrSeed1; pokeByteOff p 144 mrSeed2; pokeByteOff p 152 mrSeedStride
+    ModelMachRep1{..} -> do
+      pokeByteOff p 0 (3 :: Word32); pokeByteOff p 4 (3 * m1Replicas)
+      pokeByteOff p 112 m1MeanUpTime; pokeByteOff p 120 m1MeanRepairTime; pokeByteOff p 128 (0 :: Double)
+      pokeByteOff p 136 m1Seed1; pokeByteOff p 144 m1Seed2; pokeByteOff p 152 m1SeedStride
 
 -- | @newEventQueue@ for a whole batch of LPs (Internal/Event.hs:92-116).
 newB200Engine :: B200Model -> B200Params -> B200Specs -> IO B200Engine
@@ -118,6 +130,7 @@ loadInitialMessages (B200Engine h) model ps specs =
     let cap = case model of
                 ModelPHOLD{..}    -> fromIntegral pholdLPs * fromIntegral pholdPopulation
                 ModelMachRep2{..} -> 2 * fromIntegral mrReplicas
+                ModelMachRep1{..} -> 2 * fromIntegral m1Replicas
     allocaBytes (cap * sizeofEvent) $ \evs -> alloca $ \pn -> do
       c_tw_model_initial_events p evs (fromIntegral cap) pn >>= check h
       n <- peek pn
@@ -145,6 +158,22 @@ globalTimeB200 :: B200Engine -> IO Double
 globalTimeB200 (B200Engine h) = alloca $ \g -> do
   c_tw_gvt h g >>= check h
   realToFrac <$> peek g
+
+-- | @registerDIO@ with an external Time Server (Internal/DIO.hs:267-283): GVT follows its @GlobalTimeMessage@s from now on.
+attachTimeServerB200 :: B200Engine -> IO ()
+attachTimeServerB200 (B200Engine h) = c_tw_attach_time_server h 1 >>= check h
+
+-- | The payload of the @LocalTimeMessage@ sent in reply to @ComputeLocalTimeMessage@ (Internal/Event.hs:425-436).
+localTimeB200 :: B200Engine -> IO Double
+localTimeB200 (B200Engine h) = alloca $ \t -> do
+  c_tw_local_time h t >>= check h
+  realToFrac <$> peek t
+
+-- | @GlobalTimeMessage t@ -> @updateGlobalTime@ (Internal/Event.hs:437-449, 528-540); 'False' = ignored (above the local time).
+globalTimeMessageB200 :: B200Engine -> Double -> IO Bool
+globalTimeMessageB200 (B200Engine h) t = alloca $ \ok -> do
+  c_tw_global_time_message h (realToFrac t) ok >>= check h
+  (/= 0) <$> peek ok
 
 -- | The pair returned by @masterModel@ (tests/MachRep2DistributedReproducible.hs:214-229), per replica.
 readMachRep2 :: B200Engine -> Int -> IO [MachRepResult]
