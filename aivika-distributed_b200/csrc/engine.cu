@@ -378,8 +378,9 @@ struct Engine : EngineBase {
     Ctl *h_ctl = nullptr;                 // pinned, 2 slots
     tw_event *d_stage = nullptr; size_t stage_cap = 0;
     unsigned long long *d_tmp = nullptr;  // [2]
+    unsigned long long *d_stats = nullptr; // per-LP result staging (tw_read_lp_stats), allocated on first use
     cudaGraphExec_t graph = nullptr;
-    uint32_t graph_steps = 0;
+    uint32_t graph_steps = 0; double graph_stop = 0.0;
     void *comm = nullptr;                 // ncclComm_t
     std::vector<void *> peer_ptrs;        // opened IPC mappings
     uint64_t launches = 0;
@@ -576,7 +577,9 @@ struct Engine : EngineBase {
 
     int build_graph(uint32_t steps)
     {
-        if (graph && graph_steps == steps) return TW_OK;
+        // the kernel parameters (d, including the stop time) are baked into the captured nodes: reuse the graph as long
+        // as neither changes (a bench or a Time Server loop calls tw_run many times with the same stop time)
+        if (graph && graph_steps == steps && graph_stop == d.stop) return TW_OK;
         if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
         cudaGraph_t g = nullptr;
         TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -594,7 +597,7 @@ struct Engine : EngineBase {
         TW_CUDA(cudaStreamEndCapture(stream, &g));
         TW_CUDA(cudaGraphInstantiate(&graph, g, 0));
         TW_CUDA(cudaGraphDestroy(g));
-        graph_steps = steps;
+        graph_steps = steps; graph_stop = d.stop;
         return TW_OK;
     }
 
@@ -602,7 +605,6 @@ struct Engine : EngineBase {
     {
         if (!(until <= P.stop_time)) until = P.stop_time;
         d.stop = until;
-        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }      // d is baked into the kernel node
         const uint32_t B = P.steps_per_launch ? P.steps_per_launch : 16;
         int rc = build_graph(B); if (rc) return rc;
         Ctl c0;
@@ -697,14 +699,13 @@ struct Engine : EngineBase {
     {
         if (n < d.n_local) { err = "output arrays shorter than the local LP count"; return TW_ERR_INVALID_ARG; }
         if (d.n_local == 0) return TW_OK;
-        unsigned long long *dn = nullptr, *dh = nullptr;
-        TW_CUDA(cudaMalloc(&dn, sizeof(unsigned long long) * d.n_local));
-        TW_CUDA(cudaMalloc(&dh, sizeof(unsigned long long) * d.n_local));
+        if (!d_stats) TW_CUDA(cudaMalloc(&d_stats, 2 * sizeof(unsigned long long) * d.n_local));   // kept for the engine's life
+        unsigned long long *dn = d_stats, *dh = d_stats + d.n_local;
         k_gather_stats<M><<<grid, kBlock, 0, stream>>>(d, dn, dh); count(1);
+        TW_CUDA(cudaGetLastError());
         TW_CUDA(cudaMemcpyAsync(n_exec, dn, sizeof(uint64_t) * d.n_local, cudaMemcpyDeviceToHost, stream));
         TW_CUDA(cudaMemcpyAsync(hash, dh, sizeof(uint64_t) * d.n_local, cudaMemcpyDeviceToHost, stream));
         TW_CUDA(cudaStreamSynchronize(stream));
-        TW_CUDA(cudaFree(dn)); TW_CUDA(cudaFree(dh));
         return TW_OK;
     }
 
@@ -745,7 +746,7 @@ struct Engine : EngineBase {
         for (void *p : peer_ptrs) cudaIpcCloseMemHandle(p);
         if (comm) g_nccl.CommDestroy(comm);
         cudaFree(d.pages); cudaFree(d.saved); cudaFree(meta); cudaFree(d.ctl);
-        cudaFree(d_stage); cudaFree(d_tmp); cudaFree(d_slots); cudaFree(d_peer_slots);
+        cudaFree(d_stage); cudaFree(d_tmp); cudaFree(d_stats); cudaFree(d_slots); cudaFree(d_peer_slots);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
         if (ev_chk[0]) cudaEventDestroy(ev_chk[0]); if (ev_chk[1]) cudaEventDestroy(ev_chk[1]);

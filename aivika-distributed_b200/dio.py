@@ -302,10 +302,16 @@ class DIO:
         self._check(self.lib.tw_set_monitor(self.h, self._monitor_cb, None))
 
     # -- results
-    def lpStats(self):
-        n_exec = np.zeros(self.n_local, dtype=np.uint64); h = np.zeros(self.n_local, dtype=np.uint64)
+    def lpStats(self, out=None):
+        """Per-LP committed-event counts and trace hashes.  `out` = (n_exec, hash) preallocated uint64 arrays of at least
+        n_local entries (e.g. views of pinned memory: the device -> host copy then needs no staging)."""
+        if out is None:
+            n_exec = np.zeros(self.n_local, dtype=np.uint64); h = np.zeros(self.n_local, dtype=np.uint64)
+        else:
+            n_exec, h = out
+            assert n_exec.dtype == np.uint64 and h.dtype == np.uint64 and len(n_exec) >= self.n_local and len(h) >= self.n_local
         self._check(self.lib.tw_read_lp_stats(self.h, n_exec.ctypes.data, h.ctypes.data, self.n_local))
-        return n_exec, h
+        return n_exec[:self.n_local], h[:self.n_local]
 
     def machRepResults(self):
         first_master = ((self.lp_base + 2) // 3) * 3
