@@ -1,7 +1,7 @@
 // tw_core.cuh -- the per-LP super-step of the batched Time Warp engine (device code).
 //
-// One thread owns one logical process (LP) for one super-step.  The step is the device form of one
-// pass of `processPendingEventsCore` / `call` (Simulation/Aivika/Distributed/Optimistic/Internal/
+// One lane owns one logical process (LP) for one super-step; a warp owns one or two tiles of 32 LPs.  The step is the
+// device form of one pass of `processPendingEventsCore` / `call` (Simulation/Aivika/Distributed/Optimistic/Internal/
 // Event.hs:196-250) over a whole batch of homogeneous LPs:
 //
 //   1. fossil collection, strict `< GVT`           reduceEvents            Internal/Event.hs:639-649
@@ -9,20 +9,22 @@
 //        anti-message  -> find twin, annihilate    findAntiMessage / annihilateMessage
 //                                                                          Internal/InputMessageQueue.hs:245-279
 //        straggler     -> mark rollback position   enqueueMessage          Internal/InputMessageQueue.hs:146-160
-//   3. rollback: restore the saved state (UndoableLog.rollbackLog, Internal/UndoableLog.hs:93-118),
-//      un-process the rolled-back inputs (rollbackInputMessages :190-201) and send anti-messages
-//      (rollbackOutputMessages, Internal/OutputMessageQueue.hs:81-104) -- regenerated by replaying the
-//      pure handler on the saved pre-state, so no output queue is stored
-//   4. pop every pending event inside the optimistic window [GVT, GVT + horizon] (isTimeHorizonExceeded,
-//      Internal/Event.hs:309-324), at most `max_batch` per step, in key order, save state, run the
-//      compiled handler, scatter the sent messages into the destination inboxes
+//   3. rollback: undo the executions (rollbackLog, Internal/UndoableLog.hs:93-118) -- by reverse computation for a
+//      reversible model, from the saved pre-state otherwise --, un-process the rolled-back inputs
+//      (rollbackInputMessages :190-201) and send anti-messages (rollbackOutputMessages,
+//      Internal/OutputMessageQueue.hs:81-104), regenerated from the pre-state of each undone event: no output queue
+//   4. select the pending events inside the optimistic window [GVT, GVT + horizon] (isTimeHorizonExceeded,
+//      Internal/Event.hs:309-324) in one pass (packed-key candidate list) and execute them in key order, at most
+//      `max_batch` per step: the owner lane does the LP's state transition, the production and delivery of the
+//      messages goes through the warp's work queue (WorkQ) and runs with all 32 lanes
 //   5. contribute min(pending, sent) to the GVT reduction (getLocalTime, Internal/Event.hs:496-514)
 //
 // Per-LP storage (all in HBM, capacity `cap` = power of two slots, ring addressed by monotone indices):
 //   pages[lp][slot]  event records.  [head, head+nproc) = processed, sorted by key (the reference's
 //                    itemProcessed=True prefix of the InputMessageQueue vector); [head+nproc, consumed) =
 //                    pending, unsorted; [consumed, total) = inbox written by senders.
-//   saved[lp][slot]  state *before* the processed event in that slot (copy state saving; the UndoableLog).
+//   saved[lp][slot]  state *before* the processed event in that slot (copy state saving; the UndoableLog) -- only
+//                    for models that are not reversible.
 //   hdr[lp]          owner-private header; in[lp] = counters other LPs touch with atomics.
 // Nothing is ever moved except one swap per pop; annihilated pairs stay as tombstones that are "processed"
 // as no-ops when their time comes (what the reference does for an anti-message that arrives first,
@@ -42,12 +44,8 @@
 namespace twb {
 
 #if defined(__CUDA_ARCH__)
-TW_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
-TW_HD void     atomic_inc_noret(uint32_t *p) { atomicAdd(p, 1u); }
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 #else
-TW_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
-TW_HD void     atomic_inc_noret(uint32_t *p) { *p += 1u; }
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 #endif
 
@@ -210,19 +208,16 @@ TW_HD void fail_checked(const Dev<M> &d, Acc &acc, uint32_t code, uint32_t l, ui
 #define TW_RECONVERGE() __syncwarp()
 #define TW_NOINLINE __device__ __noinline__
 TW_HD bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
-TW_HD uint32_t ctz64(uint64_t m) { return (uint32_t)__ffsll((long long)m) - 1u; }
 TW_HD uint32_t bitlen64(uint64_t m) { return 64u - (uint32_t)__clzll((long long)m); }
 #elif defined(__CUDACC__)
 #define TW_RECONVERGE() ((void)0)
 #define TW_NOINLINE __device__ __noinline__
 TW_HD bool warp_any(bool p) { return p; }
-TW_HD uint32_t ctz64(uint64_t m) { return (uint32_t)__builtin_ctzll(m); }
 TW_HD uint32_t bitlen64(uint64_t m) { return m ? 64u - (uint32_t)__builtin_clzll(m) : 0u; }
 #else
 #define TW_RECONVERGE() ((void)0)
 #define TW_NOINLINE
 TW_HD bool warp_any(bool p) { return p; }
-TW_HD uint32_t ctz64(uint64_t m) { return (uint32_t)__builtin_ctzll(m); }
 TW_HD uint32_t bitlen64(uint64_t m) { return m ? 64u - (uint32_t)__builtin_clzll(m) : 0u; }
 #endif
 

@@ -118,6 +118,33 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     return TW_OK;
 }
 
+// building blocks of tw_dsl.cuh against the semantics of aivika-transformers' FCFS resource:
+// returns 0 when every scripted step behaves as documented, otherwise the number of the failing check.
+extern "C" int emu_dsl_selftest()
+{
+    dsl::FcfsResource<3> r; r.init(1);
+    bool granted = false, resumed = false; uint8_t w = 0;
+    if (r.request(1, granted) != H_OK || !granted || r.count != 0) return 1;          // count 1 -> granted, count 0
+    if (r.request(2, granted) != H_OK || granted || r.wait_len != 1) return 2;         // busy -> queued
+    if (r.request(3, granted) != H_OK || granted || r.wait_len != 2) return 3;
+    if (r.release(1, resumed, w) != H_OK || !resumed || w != 2 || r.count != 0 || r.wait_len != 1) return 4;   // FCFS: first waiter, count unchanged
+    if (r.release(1, resumed, w) != H_OK || !resumed || w != 3 || r.wait_len != 0) return 5;
+    if (r.release(1, resumed, w) != H_OK || resumed || r.count != 1) return 6;         // nobody waits: count' = 1
+    if (r.release(1, resumed, w) != H_RETRY || r.count != 1) return 7;                 // over-release: SimulationRetry, state untouched
+    r.init(0);
+    for (uint8_t k = 1; k <= 3; ++k) if (r.request(k, granted) != H_OK || granted) return 8;
+    if (r.request(4, granted) != H_RETRY || r.wait_len != 3) return 9;                 // wait list full: only a stale optimistic state
+    MachRepModel::Event out[4]; int n = 0; uint64_t ctr = 41;
+    dsl::Outbox<MachRepModel::Event> ob(out, n, ctr, 7, 2.5);
+    ob.enqueueMessage(9, 3.5, 5, 1.25); ob.sendMessage(3, 6, 0.0);
+    if (n != 2 || ctr != 43 || out[0].recv_ts != 3.5 || out[0].send_ts != 2.5 || out[0].ctr != 41 || out[0].src != 7 || out[0].dst != 9 ||
+        out[0].type != 5 || out[0].value != 1.25) return 10;
+    if (out[1].recv_ts != 2.5 || out[1].send_ts != 2.5 || out[1].ctr != 42 || out[1].dst != 3) return 11;    // sendMessage: receive time = now
+    StdGen g1 = mk_std_gen(456), g2 = mk_std_gen(456);
+    if (dsl::random_exponential(g1, 0.5) != expo_variate(std_random_double(g2), 0.5) || g1.s1 != g2.s1 || g1.s2 != g2.s2) return 12;
+    return 0;
+}
+
 // reverse computation: PholdModel::reverse must be the exact inverse of PholdModel::advance (returns mismatches)
 extern "C" int emu_phold_reverse_roundtrip(uint64_t seed, int n)
 {

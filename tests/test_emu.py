@@ -151,3 +151,9 @@ def test_lagging_global_time_of_an_external_time_server(H, every):
     res = H.oracle_machrep(pm)
     rc, n_exec, h, mr, _ = H.emu_run(pm, 2, gvt_every=every)
     assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop for r in range(4))
+
+
+def test_model_building_blocks(H):
+    """tw_dsl.cuh: FcfsResource follows requestResource / releaseResourceWithinEvent (FCFS hand-over, over-release =
+    SimulationRetry), Outbox follows enqueueMessage / sendMessage, random_exponential draws from the undoable StdGen."""
+    assert H.emu().emu_dsl_selftest() == 0
