@@ -675,7 +675,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     bool need_scan = live && !heavy;
     const char *pgb = reinterpret_cast<const char *>(pg);
     for (;;) {                                               // rounds: one scan, then up to kCand executions per lane
-        if (!warp_any(need_scan || (heavy && !searched))) break;
+        if (!warp_any(need_scan || (heavy && live && !searched))) break;
         if (need_scan) {
             rbase = done; mv = 0; drop = kNoCand; nleft = 0;
             const uint32_t rbeg = pbeg + done, rn = nreg - done;
@@ -766,7 +766,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
                 const uint32_t pi = done;                    // relative index of the slot being filled
                 Event e = pg[(pbeg + bix) & mask];
                 const Event x = pg[(pbeg + pi) & mask];      // its current occupant (loaded together with e)
-                if (e.recv_ts < h.lvt) { fail_checked<M>(d, acc, TW_ERR_TIME_ORDER, l, h.head_prev); live = false; stopped = true; }
+                if (e.recv_ts < h.lvt) { fail_checked<M>(d, acc, TW_ERR_TIME_ORDER, l, h.head_prev); live = false; stopped = true; searched = true; }
                 else {
                     const State before = st;
                     const bool noop = (e.ctr & (kAntiBit | kDeadBit)) != 0;

@@ -157,3 +157,14 @@ def test_model_building_blocks(H):
     """tw_dsl.cuh: FcfsResource follows requestResource / releaseResourceWithinEvent (FCFS hand-over, over-release =
     SimulationRetry), Outbox follows enqueueMessage / sendMessage, random_exponential draws from the undoable StdGen."""
     assert H.emu().emu_dsl_selftest() == 0
+
+
+@pytest.mark.timeout(120)
+def test_overflow_inside_a_long_region_is_an_error_code_not_a_hang(H):
+    """Regression: a lane searching a long pending region (whole-region search) that hits an inconsistency caused by a
+    ring overflow used to keep the warp's round loop alive for ever; it must report TW_ERR_QUEUE_OVERFLOW."""
+    p = H.phold_params(1458, 3.0, population=1, remote_pct=50, lookahead=0.0, mean=1.0, seed=177738635, n_hot=16, hot_pct=80,
+                       horizon=2.5, cap=64, batch=6)
+    for sd in (0, 11, 512):
+        rc, *_ = H.emu_run(p, sd, gvt_every=3)
+        assert rc == 5
