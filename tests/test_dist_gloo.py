@@ -1,6 +1,6 @@
 """N > 1 host path on CPU: two processes over gloo exercise exactly what bench.py does between ranks
 (ncclUniqueId hand-off, LP-range partitioning of the start-time messages, MAX/SUM reductions).  The data path
-itself has no collective except the GVT all-reduce(min); its multi-partition addressing is covered
+itself has no collective except the GVT mailbox round; its multi-partition addressing is covered
 by tests/test_emu.py::test_phold_partitioned."""
 import ctypes as C
 import os

@@ -1,5 +1,5 @@
 """Launched under torchrun by tests/test_gpu_multi.py: every rank owns a slice of the LPs, runs the engine with
-NVLink peer scatter + ncclAllReduce(min) GVT, and rank 0 checks the gathered per-LP results against the CPU oracle."""
+NVLink peer scatter + the fused GVT mailbox round, and rank 0 checks the gathered per-LP results against the CPU oracle."""
 import os
 import sys
 
