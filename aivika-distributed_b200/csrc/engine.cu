@@ -249,6 +249,17 @@ __global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_ti
     d.state[l] = M::initial_state(d.mp, d.lp_base + l);
 }
 
+// After a consistency error (unmatched anti-message, time order, outdated message): was a ring overflow the cause?  An
+// LP whose ring overflowed during a super-step notices it only at its next drain, but by then the garbage it read may
+// already have produced bogus (anti-)messages that make *other* LPs fail first.  Report the cause.
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_diagnose_overflow(const Dev<M> d)
+{
+    const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
+    if (l >= d.n_local) return;
+    if (in_total(d.in[l].word) - d.hdr[l].head > d.cap) { d.ctl->error = TW_ERR_QUEUE_OVERFLOW; d.ctl->err_lp = d.lp_base + l; }
+}
+
 template <class M>
 __global__ void __launch_bounds__(kBlock) k_collect(const Dev<M> d, unsigned long long *out /* [2] */)
 {
@@ -566,8 +577,15 @@ struct Engine : EngineBase {
         return check_device_error(h_ctl[0]);
     }
 
-    int check_device_error(const Ctl &c)
+    int check_device_error(const Ctl &c_in)
     {
+        Ctl c = c_in;
+        if (c.error == TW_ERR_ANTI_UNMATCHED || c.error == TW_ERR_TIME_ORDER || c.error == TW_ERR_OUTDATED_MESSAGE) {
+            k_diagnose_overflow<M><<<grid, kBlock, 0, stream>>>(d); count(1);
+            Ctl *tmp = &h_ctl[0];
+            if (cudaMemcpyAsync(tmp, d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+                cudaStreamSynchronize(stream) == cudaSuccess && tmp->error == TW_ERR_QUEUE_OVERFLOW) { c.error = tmp->error; c.err_lp = tmp->err_lp; }
+        }
         if (c.error) {
             char b[256]; snprintf(b, sizeof b, "%s (LP %u, step %u)", code_name((int)c.error), c.err_lp, c.step);
             err = b; return (int)c.error;

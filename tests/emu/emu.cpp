@@ -81,6 +81,12 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
         acc.init();
         for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step); }
+        if (acc.err == TW_ERR_ANTI_UNMATCHED || acc.err == TW_ERR_TIME_ORDER || acc.err == TW_ERR_OUTDATED_MESSAGE) {
+            // engine.cu k_diagnose_overflow: an overflowed ring elsewhere is the cause of such an inconsistency
+            for (uint32_t r = 0; r < W; ++r)
+                for (uint32_t l = 0; l < parts[r].d.n_local; ++l)
+                    if (in_total(parts[r].in[l].word) - parts[r].hdr[l].head > cap) { acc.err = TW_ERR_QUEUE_OVERFLOW; acc.err_lp = parts[r].d.lp_base + l; }
+        }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
         const double g = std::min(acc.pend_min, acc.emit_min);
         if (g < local_min) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", local_min, g, step); return 100; }
