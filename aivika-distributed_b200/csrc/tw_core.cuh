@@ -711,8 +711,9 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             for (int i = 0; i + 1 < kCand; ++i)
                 if (c[i + 1] != kNoCand && (c[i] >> 5) == (c[i + 1] >> 5))
                     tie = tie || !tie_is_harmless<M>(pg, mask, rbeg, c[i] & 31u, c[i + 1] & 31u);
-            if (drop != kNoCand && (c[kCand - 1] >> 5) == (drop >> 5))
-                tie = tie || !tie_is_harmless<M>(pg, mask, rbeg, c[kCand - 1] & 31u, drop & 31u);
+            // the last candidate shares its quantum with an entry that did not fit into the list: `drop` is only the
+            // first of possibly several such entries, so no harmless-pair shortcut here
+            if (drop != kNoCand && (c[kCand - 1] >> 5) == (drop >> 5)) tie = true;
             if (tie) { heavy = true; searched = false; }
             need_scan = false;
         }

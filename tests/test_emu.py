@@ -168,3 +168,19 @@ def test_overflow_inside_a_long_region_is_an_error_code_not_a_hang(H):
     for sd in (0, 11, 512):
         rc, *_ = H.emu_run(p, sd, gvt_every=3)
         assert rc == 5
+
+
+def test_quantum_tie_across_the_candidate_list_boundary(H):
+    """Regression (found by tools/stress_emu.py): three entries in one time quantum, two of them a tombstone pair -- the
+    last candidate and the first dropped entry looked like a harmless pair, a third, earlier entry behind them was executed
+    too late (TW_ERR_TIME_ORDER).  A tie across the list boundary must always take the exact search."""
+    p = H.machrep_params(4, 120.0, horizon=-1.0, cap=256, batch=16, world=2, seed1=79928, seed2=149933)
+    res = H.oracle_machrep(p)
+    for sd in (1, 2, 3, 5, 8):
+        rc, n_exec, h, mr, _ = H.emu_run(p, sd, gvt_every=5)
+        assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop for r in range(4))
+    p = H.machrep_params(11, 120.0, horizon=-1.0, cap=1024, batch=16, seed1=582035, seed2=504955)
+    res = H.oracle_machrep(p)
+    for sd in (0, 4, 7):
+        rc, n_exec, h, mr, _ = H.emu_run(p, sd)
+        assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop for r in range(11))
