@@ -810,10 +810,16 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     }
     // what stays pending inside the window (batch limit, retry, throttle) still bounds GVT: the earliest such entry
     if (live && !heavy && nleft > 0) {
-        uint32_t ix = (c[0] != kNoCand ? c[0] : drop) & 31u;
-        const uint32_t rd = done - rbase;
-        while (ix < rd) ix = (mv >> (5u * ix)) & 31u;
-        rest_min = dmin(rest_min, pg[(pbeg + rbase + ix) & mask].recv_ts);
+        if (c[0] != kNoCand) {                               // the list's head is its exact minimum (ties were ruled out)
+            uint32_t ix = c[0] & 31u;
+            const uint32_t rd = done - rbase;
+            while (ix < rd) ix = (mv >> (5u * ix)) & 31u;
+            rest_min = dmin(rest_min, pg[(pbeg + rbase + ix) & mask].recv_ts);
+        } else {
+            // only entries that did not fit into the list are left: `drop` names the earliest quantum among them, but
+            // not necessarily the earliest entry inside that quantum -- take the quantum's lower bound (still >= gvt)
+            rest_min = dmin(rest_min, bits2d(gbits + ((uint64_t)(drop >> 5) << qshift)));
+        }
     }
     TW_RECONVERGE();
     // (the caller drains the work queue: a warp that runs several tiles of LPs carries a partly filled queue over)
