@@ -424,6 +424,8 @@ struct Engine : EngineBase {
         d.cap = cap; d.mask = cap - 1; d.max_batch = mb;
         d.proc_limit = p.proc_limit ? p.proc_limit : cap / 4;
         d.fossil_thresh = p.fossil_threshold ? p.fossil_threshold : cap / 8;
+        // fossil collection must set in before the throttle does, or a throttled LP only ever advances one event per GVT
+        if (d.fossil_thresh > d.proc_limit / 2) d.fossil_thresh = d.proc_limit / 2 ? d.proc_limit / 2 : 1;
         d.stop = p.stop_time;
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);

@@ -44,6 +44,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : 8;
         d.proc_limit = p->proc_limit ? p->proc_limit : cap / 4;
         d.fossil_thresh = p->fossil_threshold ? p->fossil_threshold : cap / 8;
+        if (d.fossil_thresh > d.proc_limit / 2) d.fossil_thresh = d.proc_limit / 2 ? d.proc_limit / 2 : 1;      // as Engine::init
         d.stop = p->stop_time; d.horizon = (p->time_horizon >= 0.0) ? p->time_horizon : -1.0;
         d.mp = M::make_params(*p);
         const size_t nl = std::max<size_t>(d.n_local, 1);
