@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(kBlock) k_diagnose_overflow(const Dev<M> d)
 {
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
     if (l >= d.n_local) return;
-    if (in_total(d.in[l].word) - d.hdr[l].head > d.cap) { d.ctl->error = TW_ERR_QUEUE_OVERFLOW; d.ctl->err_lp = d.lp_base + l; }
+    // the same conservative rule as the LP's own check: everything reserved so far against the head at the start of the
+    // LP's last completed step (senders of that step may have raced with its fossil collection)
+    if (in_total(d.in[l].word) - d.hdr[l].head_prev > d.cap) { d.ctl->error = TW_ERR_QUEUE_OVERFLOW; d.ctl->err_lp = d.lp_base + l; }
 }
 
 template <class M>
@@ -667,6 +669,9 @@ struct Engine : EngineBase {
         for (int s = 0; s < 2; ++s) if (pending[s]) { last = h_ctl[s].c_steps >= last.c_steps ? h_ctl[s] : last; }
         if (result == TW_OK) result = check_device_error(last);
         float ms = 0.f; TW_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        // An overflow of the last super-steps has no next drain that would notice it: check every ring once more before
+        // the results are handed out (the kernel turns an overflow into the engine's error state).
+        if (result == TW_OK) { k_diagnose_overflow<M><<<grid, kBlock, 0, stream>>>(d); count(1); }
         // final control block + committed totals
         TW_CUDA(cudaMemsetAsync(d_tmp, 0, 2 * sizeof(unsigned long long), stream));
         k_collect<M><<<grid < 1184 ? grid : 1184, kBlock, 0, stream>>>(d, d_tmp); count(1);
