@@ -41,10 +41,21 @@
 #pragma once
 #include "tw_models.cuh"
 
+// TW_SIMT: the warp-level code paths (work queue, whole-warp search, reconvergence).  They are what the GPU runs; a host
+// build can select them too (-DTW_SIMT_EMU, tests/emu/simt.hpp: 32 host threads play the lanes of a warp and the warp
+// intrinsics are rendezvous points), so that the very code the device executes is tested against the oracle on the CPU.
+#if defined(__CUDA_ARCH__) || defined(TW_SIMT_EMU)
+#define TW_SIMT 1
+#else
+#define TW_SIMT 0
+#endif
+
 namespace twb {
 
 #if defined(__CUDA_ARCH__)
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+#elif defined(TW_SIMT_EMU)
+TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 #else
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 #endif
@@ -209,6 +220,11 @@ TW_HD void fail_checked(const Dev<M> &d, Acc &acc, uint32_t code, uint32_t l, ui
 #define TW_NOINLINE __device__ __noinline__
 TW_HD bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 TW_HD uint32_t bitlen64(uint64_t m) { return 64u - (uint32_t)__clzll((long long)m); }
+#elif defined(TW_SIMT_EMU)
+#define TW_RECONVERGE() __syncwarp()
+#define TW_NOINLINE
+TW_HD bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+TW_HD uint32_t bitlen64(uint64_t m) { return 64u - (uint32_t)__clzll((long long)m); }
 #elif defined(__CUDACC__)
 #define TW_RECONVERGE() ((void)0)
 #define TW_NOINLINE __device__ __noinline__
@@ -252,7 +268,7 @@ struct WorkQ {
     static_assert(sizeof(Event) % 16 == 0, "event records are held in 16-byte granules");
     // shared memory of one warp: the queue, then the held events (lane-interleaved granules), then their ring pointers
     static constexpr size_t kWarpBytes = kQueueSlots * sizeof(Work) + (size_t)M::kMaxSends * 32 * (sizeof(Event) + 8);
-#if defined(__CUDA_ARCH__)
+#if TW_SIMT
     Work *buf;                       // this warp's ring of kQueueSlots items in shared memory
     uint32_t head, tail;             // warp-uniform monotone indices
     // Deferred delivery: the messages a lane produces in one flush are held in shared memory while their slot
@@ -358,9 +374,11 @@ TW_NOINLINE void drain_slow(const Dev<M> &d, Acc &acc, StepCtx<M> &c, uint32_t l
     for (uint32_t a = c.consumed0; a != consumed; ++a) {
         const Event e = pg[a & mask];
         if (e.ctr & kAntiBit) {
-            // find the positive twin among everything older, newest first.  Among live entries there is at most one
-            // older copy besides a re-sent one of the same super-step, and the copies of a message are identical.
-            uint32_t b = a; bool found = false;
+            // find the positive twin, newest first, among what arrived in EARLIER super-steps: an anti-message is sent at
+            // least one step after its twin, and there is at most one live copy there.  The arrivals of this step are
+            // no candidates: the copy re-sent by the rolled-back sender can carry the same identity (counter, times) with
+            // a different payload and, the deliveries of one flush being unordered, may sit in front of the anti-message.
+            uint32_t b = c.consumed0; bool found = false;
             while (b != head) {
                 --b;
                 const Event m = pg[b & mask];
@@ -444,7 +462,7 @@ TW_NOINLINE uint32_t min_by_full_key(const typename M::Event *pg, uint32_t mask,
     return best;
 }
 
-#if defined(__CUDA_ARCH__)
+#if TW_SIMT
 // Cooperative search of a long pending region (more than kMaskBits entries): the whole warp looks for the
 // earliest record of the leader's region, 32 records per load.  All lanes call it with the leader's arguments;
 // the result is meaningful on every lane.  `tie` reports that the minimum receive time occurs more than once.
@@ -726,7 +744,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             if (!warp_any(want)) break;
             uint32_t bix = 0; double bts = pos_inf();
             // heavy lanes: earliest record of [pbeg + done, consumed), found by the whole warp
-#if defined(__CUDA_ARCH__)
+#if TW_SIMT
             for (unsigned hm = __ballot_sync(0xffffffffu, want && heavy); hm; hm &= hm - 1u) {
                 const int leader = __ffs(hm) - 1;
                 const Event *lpg = reinterpret_cast<const Event *>(__shfl_sync(0xffffffffu, (unsigned long long)pg, leader));

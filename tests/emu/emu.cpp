@@ -6,10 +6,18 @@
 // the exact source the GPU runs, in a container that has no GPU, and exercise the multi-partition (world > 1)
 // addressing without NVLink.  It is a development aid and a `-m "not gpu"` test of the host-side logic; parity
 // claims are made only by the `-m gpu` tests that call the CUDA build through the C ABI.
+//
+// Two builds (tests/helpers.py): libtwemu.so runs the scalar paths LP by LP; libtwemu_simt.so (-DTW_SIMT_EMU) runs the
+// warp-level device paths -- work queue with deferred delivery, whole-warp region search, reconvergence points -- with 32
+// host threads as the lanes of a warp (simt.hpp), one warp at a time.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+#ifdef TW_SIMT_EMU
+#include "simt.hpp"
+#endif
 #include "../../aivika-distributed_b200/csrc/tw_core.cuh"
 
 using namespace twb;
@@ -25,9 +33,45 @@ struct Part {
 
 static uint64_t rng_next(uint64_t &s) { s += kGolden; return mix_fin(s); }
 
+#ifdef TW_SIMT_EMU
+// 32 lane threads that run one warp-visit (d.tiles tiles of 32 LPs, then the queue drain) per job, like k_step does.
+template <class M>
+struct WarpPool {
+    simt::Warp warp;
+    simt::Barrier start{33}, done{33};
+    std::vector<std::thread> lanes;
+    std::vector<char> smem;
+    Acc accs[32];
+    const Dev<M> *d = nullptr; uint32_t tile0 = 0; double gvt = 0, wend = 0; uint32_t step = 0; bool quit = false;
+    WarpPool() : smem(WorkQ<M>::kWarpBytes + 16)
+    {
+        for (unsigned lane = 0; lane < 32; ++lane) lanes.emplace_back([this, lane] {
+            simt::g_warp = &warp; simt::g_lane = lane; threadIdx.x = lane;
+            for (;;) {
+                start.wait();
+                if (quit) return;
+                Acc a; a.init();
+                WorkQ<M> q; q.init((void *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15));
+                for (uint32_t t = 0; t < d->tiles; ++t) lp_step<M>(*d, a, q, (tile0 + t) * 32u + lane, gvt, wend, step);
+                q.drain(*d, a, step & 1u);
+                accs[lane] = a;
+                done.wait();
+            }
+        });
+    }
+    void run(const Dev<M> &dev, uint32_t first_tile, double g, double w, uint32_t s, Acc &acc)
+    {
+        d = &dev; tile0 = first_tile; gvt = g; wend = w; step = s;
+        start.wait(); done.wait();
+        for (int i = 0; i < 32; ++i) acc.merge(accs[i]);
+    }
+    ~WarpPool() { quit = true; start.wait(); for (auto &t : lanes) t.join(); }
+};
+#endif
+
 template <class M>
 static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,
-                     tw_machrep_result *mr, tw_run_stats *st, uint32_t gvt_every = 1)
+                     tw_machrep_result *mr, tw_run_stats *st, uint32_t gvt_every = 1, uint32_t tiles = 1)
 {
     const uint32_t W = p->world ? p->world : 1;
     if (W > (uint32_t)kMaxWorld) return TW_ERR_INVALID_ARG;
@@ -40,7 +84,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         memset(&d, 0, sizeof d);
         d.n_global = p->n_lps; d.world = W; d.rank = r; d.n_per = n_per; d.lp_base = n_per * r;
         d.n_local = d.lp_base >= p->n_lps ? 0 : std::min(n_per, p->n_lps - d.lp_base);
-        d.cap = cap; d.mask = cap - 1; d.tiles = 1;
+        d.cap = cap; d.mask = cap - 1; d.tiles = tiles ? tiles : 1;
         d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : 8;
         d.proc_limit = p->proc_limit ? p->proc_limit : cap / 4;
         d.fossil_thresh = p->fossil_threshold ? p->fossil_threshold : cap / 8;
@@ -71,7 +115,13 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     gvt = std::min(gvt, acc.emit_min);
 
     std::vector<std::pair<uint32_t, uint32_t>> order;
+#ifdef TW_SIMT_EMU
+    WarpPool<M> pool;                       // order = (partition, first tile of a warp)
+    for (uint32_t r = 0; r < W; ++r)
+        for (uint32_t t = 0; t * 32u < std::max<uint32_t>(parts[r].d.n_local, 1u); t += parts[r].d.tiles) order.push_back({r, t});
+#else
     for (uint32_t r = 0; r < W; ++r) for (uint32_t l = 0; l < parts[r].d.n_local; ++l) order.push_back({r, l});
+#endif
     uint64_t rs = shuffle_seed;
     tw_run_stats S; memset(&S, 0, sizeof S);
     uint64_t stall = 0;
@@ -81,7 +131,11 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
         if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
         acc.init();
+#ifdef TW_SIMT_EMU
+        for (auto &o : order) pool.run(parts[o.first].d, o.second, gvt, wend, step, acc);
+#else
         for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step); }
+#endif
         if (acc.err == TW_ERR_ANTI_UNMATCHED || acc.err == TW_ERR_TIME_ORDER || acc.err == TW_ERR_OUTDATED_MESSAGE) {
             // engine.cu k_diagnose_overflow: an overflowed ring elsewhere is the cause of such an inconsistency
             for (uint32_t r = 0; r < W; ++r)
@@ -89,6 +143,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
                     if (in_total(parts[r].in[l].word) - parts[r].hdr[l].head_prev > cap) { acc.err = TW_ERR_QUEUE_OVERFLOW; acc.err_lp = parts[r].d.lp_base + l; }
         }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
+        if (getenv("EMU_TRACE")) fprintf(stderr, "step %u gvt %.17g exec %u rb %u rollbacks %u strag %u anti %u annih %u retry %u sent %u pend %.17g emit %.17g\n", step, gvt, acc.exec, acc.rb_events, acc.rollbacks, acc.strag, acc.anti, acc.annih, acc.retry, acc.sent_local + acc.sent_remote, acc.pend_min, acc.emit_min);
         const double g = std::min(acc.pend_min, acc.emit_min);
         if (g < local_min) { fprintf(stderr, "emu: GVT went backwards %.17g -> %.17g at step %u\n", local_min, g, step); return 100; }
         if (g == local_min) { if (++stall > 100000) return TW_ERR_DEADLOCK; } else stall = 0;
@@ -185,6 +240,25 @@ extern "C" int emu_run_lagged(const tw_params *p, uint64_t shuffle_seed, uint32_
     if (p->model == TW_MODEL_MACHREP2) return emu_run_t<MachRepModel>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every);
     if (p->model == TW_MODEL_MACHREP1) return emu_run_t<MachRep1Model>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every);
     return TW_ERR_INVALID_ARG;
+}
+
+// warp-level build: LP tiles per warp as in Engine::init (the work queue is carried from tile to tile)
+extern "C" int emu_run_tiles(const tw_params *p, uint64_t shuffle_seed, uint32_t gvt_every, uint32_t tiles, uint64_t *n_exec,
+                             uint64_t *hash, tw_machrep_result *mr, tw_run_stats *st)
+{
+    if (gvt_every == 0) gvt_every = 1;
+    if (p->model == TW_MODEL_PHOLD) return emu_run_t<PholdModel>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every, tiles);
+    if (p->model == TW_MODEL_MACHREP2) return emu_run_t<MachRepModel>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every, tiles);
+    if (p->model == TW_MODEL_MACHREP1) return emu_run_t<MachRep1Model>(p, shuffle_seed, n_exec, hash, mr, st, gvt_every, tiles);
+    return TW_ERR_INVALID_ARG;
+}
+extern "C" int emu_is_simt(void)
+{
+#ifdef TW_SIMT_EMU
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 extern "C" int emu_run(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec, uint64_t *hash,

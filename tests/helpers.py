@@ -106,7 +106,7 @@ def emu():
     if _emu is None:
         d = os.path.join(ROOT, "tests", "emu")
         so = os.path.join(d, "libtwemu.so")
-        srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(PKG_DIR, "csrc", f) for f in ("tw_core.cuh", "tw_models.cuh", "tw_math.cuh")]
+        srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(PKG_DIR, "csrc", f) for f in ("tw_core.cuh", "tw_models.cuh", "tw_math.cuh", "tw_dsl.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                             os.path.join(d, "emu.cpp"), "-o", so], check=True)
@@ -185,6 +185,39 @@ def oracle_machrep(p, r0=0, r1=None):
     rc = oracle().oracle_machrep_run(C.byref(op), r0, r1, res, None, 0, None)
     assert rc == 0, rc
     return res
+
+
+_emu_simt = None
+
+
+def emu_simt():
+    """The warp-level build of the same file (-DTW_SIMT_EMU): 32 host threads play the lanes of a warp (tests/emu/simt.hpp),
+    so the device code paths -- work queue, deferred delivery, whole-warp search -- run on the CPU."""
+    global _emu_simt
+    if _emu_simt is None:
+        d = os.path.join(ROOT, "tests", "emu")
+        so = os.path.join(d, "libtwemu_simt.so")
+        srcs = [os.path.join(d, "emu.cpp"), os.path.join(d, "simt.hpp")] + \
+               [os.path.join(PKG_DIR, "csrc", f) for f in ("tw_core.cuh", "tw_models.cuh", "tw_math.cuh", "tw_dsl.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-DTW_SIMT_EMU",
+                            "-x", "c++", os.path.join(d, "emu.cpp"), "-o", so], check=True)
+        L = C.CDLL(so)
+        L.emu_run_tiles.argtypes = [C.POINTER(ffi.tw_params), C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(ffi.tw_run_stats)]
+        L.emu_run_tiles.restype = C.c_int
+        assert L.emu_is_simt() == 1
+        _emu_simt = L
+    return _emu_simt
+
+
+def emu_simt_run(p, shuffle_seed=1, gvt_every=1, tiles=1):
+    import numpy as np
+    n_exec = np.zeros(p.n_lps, dtype=np.uint64); h = np.zeros(p.n_lps, dtype=np.uint64)
+    mr = (ffi.tw_machrep_result * max(1, p.n_lps // 3))()
+    st = ffi.tw_run_stats()
+    rc = emu_simt().emu_run_tiles(C.byref(p), shuffle_seed, gvt_every, tiles, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
+    return rc, n_exec, h, mr, st
 
 
 def emu_run(p, shuffle_seed=1, gvt_every=1):

@@ -184,3 +184,44 @@ def test_quantum_tie_across_the_candidate_list_boundary(H):
     for sd in (0, 4, 7):
         rc, n_exec, h, mr, _ = H.emu_run(p, sd)
         assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop for r in range(11))
+
+
+# ---------------------------------------------------------------- the warp-level build (tests/emu/simt.hpp)
+def check_phold_simt(H, p, tiles=1, seeds=(0, 3)):
+    n_exec, h, s = H.oracle_phold(p)
+    for sd in seeds:
+        rc, e_exec, e_hash, _, stats = H.emu_simt_run(p, sd, 1, tiles)
+        assert rc == 0 and (e_exec == n_exec).all() and (e_hash == h).all() and stats.committed == s.committed
+    return stats
+
+
+@pytest.mark.parametrize("tiles", [1, 2, 3])
+def test_warp_level_paths_phold(H, tiles):
+    """The code a GPU warp runs -- work queue with deferred delivery, warp-uniform loops, whole-warp search of long
+    regions, tie fallbacks, tiles carried through one queue -- executed by 32 host threads as lanes, against the oracle."""
+    st_ = check_phold_simt(H, H.phold_params(300, 4.0, remote_pct=50, horizon=0.5, batch=8, cap=256), tiles)
+    assert st_.rolled_back > 0 and st_.anti_sent > 0
+    check_phold_simt(H, H.phold_params(128, 3.0, population=8, remote_pct=80, n_hot=2, hot_pct=60, horizon=1.0, cap=2048, batch=8,
+                                       proc_limit=512), tiles, seeds=(1,))
+    check_phold_simt(H, H.phold_params(200, 3.0, population=6, remote_pct=30, lookahead=0.5, mean=0.0, horizon=-1.0, batch=4,
+                                       cap=512), tiles, seeds=(2,))
+    check_phold_simt(H, H.phold_params(500, 3.0, remote_pct=50, horizon=0.7, world=3, batch=6, cap=256), tiles, seeds=(4,))
+
+
+@pytest.mark.parametrize("horizon,batch", [(-1.0, 4), (0.5, 4), (2.0, 8), (0.0, 4)])
+def test_warp_level_paths_machrep(H, horizon, batch):
+    """Regression: the deliveries of one queue flush are unordered, so the copy a rolled-back sender re-sends (same
+    counter and times, possibly another payload) can land in front of the anti-message of the old copy; the anti-message
+    must annihilate the copy of an EARLIER step, not the newest one (found with this build: wrong MachRep2 statistics)."""
+    p = H.machrep_params(3, 40.0, horizon=horizon, batch=batch, cap=256)
+    res = H.oracle_machrep(p)
+    for sd in (0, 1, 2):
+        rc, n_exec, h, mr, _ = H.emu_simt_run(p, sd, 1, 1)
+        assert rc == 0
+        for r in range(3):
+            assert res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop
+            assert [res[r].hash[k] for k in range(3)] == [int(h[3 * r + k]) for k in range(3)]
+    p1 = H.machrep1_params(3, 60.0, horizon=horizon, batch=batch, cap=512)
+    r1 = H.oracle_machrep1(p1)
+    rc, n_exec, h, mr, _ = H.emu_simt_run(p1, 1, 1, 2)
+    assert rc == 0 and all(r1[r].up_time_prop == mr[r].up_time_prop for r in range(3))

@@ -1,6 +1,7 @@
 """Randomized stress of the engine logic on the CPU: tests/emu (the device functions compiled with g++) against the
 sequential oracle over random PHOLD / MachRep2 / MachRep1 configurations (window, batch, ring size, skew, partitions,
-lagging GVT).  Usage: python tools/stress_emu.py <seed> <seconds> [fast].  Ring overflows are legitimate outcomes;
+lagging GVT).  Usage: python tools/stress_emu.py <seed> <seconds> [fast] [simt].  `simt` runs the warp-level build (32 host
+threads as the lanes of a warp: work queue, deferred delivery, whole-warp search; random tiles per warp).  Ring overflows are legitimate outcomes;
 `fast` keeps every case small (used by tests/test_stress_short.py).  Exit status 1 when a case fails."""
 import sys, time
 import os; sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
@@ -8,7 +9,12 @@ import helpers as H, numpy as np
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv)>1 else 1)
 t0=time.time(); n_ok=0; n_over=0; fails=[]
 budget=float(sys.argv[2]) if len(sys.argv)>2 else 300
-fast = len(sys.argv) > 3 and sys.argv[3] == 'fast'
+fast = 'fast' in sys.argv[3:]
+simt = 'simt' in sys.argv[3:]
+def run_emu(p, sd, every):
+    if simt:
+        return H.emu_simt_run(p, sd, every, int(rng.choice([1, 1, 2, 3])))
+    return H.emu_run(p, sd, gvt_every=every)
 while time.time()-t0 < budget:
     kind = rng.integers(0,10)
     if kind < 7:
@@ -27,7 +33,7 @@ while time.time()-t0 < budget:
         desc = dict(n=n,pop=pop,rp=rp,hz=hz,batch=batch,n_hot=n_hot,hot=hot,la=la,mean=mean,cap=cap,world=world,pl=pl,fo=fo,seed=seed,T=T,every=every)
         print("case", desc, flush=True)
         o_exec,o_hash,o_sum = H.oracle_phold(p)
-        rc,e,eh,_,st = H.emu_run(p, int(rng.integers(0,1000)), gvt_every=every)
+        rc,e,eh,_,st = run_emu(p, int(rng.integers(0,1000)), every)
         if rc == 5: n_over += 1; continue
         ok = rc==0 and (e==o_exec).all() and (eh==o_hash).all() and st.executed-st.rolled_back==st.committed
     else:
@@ -41,7 +47,7 @@ while time.time()-t0 < budget:
             p = H.machrep1_params(nrep, T, horizon=hz, cap=cap, batch=batch, world=world, seed1=s1, seed2=s2); res = H.oracle_machrep1(p)
         else:
             p = H.machrep_params(nrep, T, horizon=hz, cap=cap, batch=batch, world=world, seed1=s1, seed2=s2); res = H.oracle_machrep(p)
-        rc,ne,h,mr,st = H.emu_run(p, int(rng.integers(0,1000)), gvt_every=every)
+        rc,ne,h,mr,st = run_emu(p, int(rng.integers(0,1000)), every)
         if rc == 5: n_over += 1; continue
         ok = rc==0 and all(res[r].up_time_prop==mr[r].up_time_prop and res[r].total_up_time==mr[r].total_up_time and
                            [res[r].hash[k] for k in range(3)]==[int(h[3*r+k]) for k in range(3)] for r in range(nrep))
