@@ -15,6 +15,8 @@ TW_OK = 0
 TW_MODEL_PHOLD = 1
 TW_MODEL_MACHREP2 = 2
 TW_MODEL_MACHREP1 = 3
+TW_FLAG_SKIP_OUTDATED = 1
+TW_FLAG_NO_GROUP_KERNEL = 2
 
 ERROR_NAMES = {
     0: "TW_OK", 1: "TW_ERR_INVALID_ARG", 2: "TW_ERR_CUDA", 3: "TW_ERR_SEND_AFTER_RECV",
@@ -27,7 +29,7 @@ ERROR_NAMES = {
 EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
     "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range",
-    "tw_attach_time_server", "tw_local_time", "tw_global_time_message",
+    "tw_attach_time_server", "tw_local_time", "tw_global_time_message", "tw_skipped_outdated",
     "tw_nccl_unique_id", "tw_last_error", "tw_strerror", "tw_version", "tw_kernel_launch_count",
 ]
 
@@ -53,7 +55,8 @@ class tw_params(C.Structure):
                 ("steps_per_launch", C.c_uint32), ("start_time", C.c_double), ("stop_time", C.c_double),
                 ("time_horizon", C.c_double), ("proc_limit", C.c_uint32), ("fossil_threshold", C.c_uint32),
                 ("outbox_capacity", C.c_uint32), ("flags", C.c_uint32), ("phold", tw_phold_params),
-                ("machrep", tw_machrep_params), ("nccl_id", C.c_uint8 * 128)]
+                ("machrep", tw_machrep_params), ("nccl_id", C.c_uint8 * 128),
+                ("sync_timeout_ms", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class tw_run_stats(C.Structure):
@@ -115,6 +118,7 @@ def load(path=None):
     lib.tw_attach_time_server.argtypes = [H, C.c_int]; lib.tw_attach_time_server.restype = C.c_int
     lib.tw_local_time.argtypes = [H, C.POINTER(C.c_double)]; lib.tw_local_time.restype = C.c_int
     lib.tw_global_time_message.argtypes = [H, C.c_double, C.POINTER(C.c_int)]; lib.tw_global_time_message.restype = C.c_int
+    lib.tw_skipped_outdated.argtypes = [H, C.POINTER(C.c_uint64)]; lib.tw_skipped_outdated.restype = C.c_int
     lib.tw_partition.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; lib.tw_partition.restype = C.c_int
     lib.tw_model_initial_events.argtypes = [C.POINTER(tw_params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.tw_model_initial_events.restype = C.c_int

@@ -1,17 +1,22 @@
 // engine.cu -- sm_100a kernels, host-side engine and the C ABI of libtwb200.so.
 //
 // Kernels (all hand-written, one thread per logical process, HBM-bound integer/f64 work):
-//   k_step<M>     one super-step of every LP of this partition (tw_core.cuh::lp_step), followed by the
-//                 in-kernel GVT reduction: warp shuffle min -> one atomicMin per block -> the last block
-//                 publishes GVT (Samadi's round trip through the Time Server,
-//                 Simulation/Aivika/Distributed/Optimistic/Internal/TimeServer.hs:369-421, collapses into this)
-//   k_route<M>    host-injected messages (enqueueMessage from runEventInStartTime / QueueMessageBulk) -> inboxes
-//   k_init<M>     newEventQueue for every LP (Internal/Event.hs:92-116)
-//   k_collect<M>  committed-event count and trace-hash sum
-// Multi-GPU: LP ranges are sharded (LP i lives on rank i / n_per); remote sends are direct NVLink peer
-// stores + peer atomics issued from inside k_step (no staging, no separate exchange kernel), and GVT is a
-// peer-memory mailbox exchange run by the last block of k_step (gvt_exchange_warp); NCCL is used for set-up and the
-// collective host-side barriers only.
+//   k_step<M>        one super-step of every LP of this partition (tw_core.cuh::lp_step), followed by the
+//                    in-kernel GVT reduction: warp shuffle min -> one atomicMin per block -> the last block
+//                    publishes GVT (Samadi's round trip through the Time Server,
+//                    Simulation/Aivika/Distributed/Optimistic/Internal/TimeServer.hs:369-421, collapses into this)
+//   k_run_groups<M>  models whose LPs form closed groups (MachRep1/2 replicas: kGroup = 3): a warp owns a few groups and
+//                    runs their super-steps back to back inside ONE launch, every group with its own GVT -- the same
+//                    lp_step, no grid-wide step per causal hop
+//   k_deliver<M>     multi-GPU: routes the staging rings the other GPUs filled during the previous super-step into the
+//                    inboxes of this partition's LPs (the inbox relay of Internal/DIO.hs:355-370)
+//   k_route<M>       host-injected messages (enqueueMessage from runEventInStartTime / QueueMessageBulk) -> inboxes
+//   k_init<M>        newEventQueue for every LP (Internal/Event.hs:92-116)
+//   k_collect<M>     committed-event count and trace-hash sum
+// Multi-GPU: LP ranges are sharded (LP i lives on rank i / n_per).  A message for another GPU is a peer store over
+// NVLink into a staging ring in the receiver's memory; the slot comes from a sender-local counter (warp-aggregated, no
+// atomic crosses NVLink) and the count travels with the GVT mailbox entry.  GVT is a peer-memory mailbox exchange run by
+// the last block of k_step (gvt_exchange_warp); NCCL is used for set-up and the collective host-side barriers only.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -19,7 +24,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -27,7 +36,7 @@
 
 namespace twb {
 
-// Launch shape of k_step, chosen by the sweep in profiles/r1_tuning.md (tools/sweep_variants.sh)
+// Launch shape of k_step, chosen by the sweep in profiles/r1_tuning.md
 #ifndef TW_BLOCK
 #define TW_BLOCK 128
 #endif
@@ -48,17 +57,22 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     }
     return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
 
 enum { C_EXEC = 0, C_RB, C_ROLLBACKS, C_STRAG, C_ANTI, C_ANNIH, C_RETRY, C_SLOCAL, C_SREMOTE, C_FOSSIL, C_COUNT };
 
-// Cross-GPU GVT, run by one warp: every rank publishes its local minimum for step `tag` into the mailbox of every peer
-// (NVLink peer stores) and waits until all `world` entries for that step have arrived, then takes the minimum -- the
-// LocalTimeMessage / GlobalTimeMessage round of the Time Server (Internal/TimeServer.hs:253-270, 384-421) without a
-// server and without NCCL on the per-step path (an 8-byte ncclAllReduce costs ~20-40 us, this ~5 us).  It is also the
-// barrier that orders the peer stores of super-step s before the loads of super-step s+1.  Waits are bounded so that a
-// lost peer becomes an error code, never a hang.  One rank per GPU is required (and enforced by the host).
-__device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer_slots, uint32_t rank, uint32_t world,
-                                                  uint32_t tag, double local_min)
+// Cross-GPU GVT, run by one warp: every rank publishes its local minimum for step `tag` -- and the number of messages it
+// staged for that peer during the step -- into the mailbox of every peer (NVLink peer stores) and waits until all `world`
+// entries for that step have arrived, then takes the minimum: the LocalTimeMessage / GlobalTimeMessage round of the Time
+// Server (Internal/TimeServer.hs:253-270, 384-421) without a server and without NCCL on the per-step path (an 8-byte
+// ncclAllReduce costs ~20-40 us, this ~5 us).  It is also the barrier that orders the peer stores of super-step s
+// before the loads of super-step s+1.  The wait is bounded by wall-clock time (globaltimer; tw_params / TWB200_PEER_TIMEOUT_MS)
+// so that a lost peer becomes an error code, never a hang.  One rank per GPU is required (and enforced by the host).
+__device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer_slots, uint32_t *stage_cnt, uint32_t rank,
+                                                  uint32_t world, uint32_t tag, double local_min, unsigned long long timeout_ns)
 {
     const uint32_t r = threadIdx.x & 31u;
     const uint32_t par = tag & 1u;
@@ -70,18 +84,25 @@ __device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer
             *(volatile uint32_t *)&(peer_slots[r] + 1 * kMaxWorld + rank)->tag = kSlotAbort;
         } else {
             *(volatile double *)&dst->value = local_min;
+            *(volatile uint32_t *)&dst->count = *(volatile uint32_t *)&stage_cnt[r * kCntStride];   // staged for rank r
             __threadfence_system();
             *(volatile uint32_t *)&dst->tag = tag;
         }
+        *(volatile uint32_t *)&stage_cnt[r * kCntStride] = 0u;           // the next step starts a fresh ring
     }
     if (aborted) return;
     double v = pos_inf(); uint32_t bad = 0;
     if (r < world) {
         const GvtSlot *src = peer_slots[rank] + par * kMaxWorld + r;      // rank r's entry in my mailbox
         uint32_t t = *(volatile const uint32_t *)&src->tag, spins = 0;
+        unsigned long long t0 = 0;
         while (t != tag) {
             if (t == kSlotAbort) { bad = TW_ERR_CUDA; break; }
-            if (++spins > 4000000u) { bad = TW_ERR_DEADLOCK; break; }     // seconds: a peer is gone
+            if ((++spins & 1023u) == 0u) {                                 // wall clock, not iterations: clocks and sleeps vary
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > timeout_ns) { bad = TW_ERR_DEADLOCK; break; }
+            }
             __nanosleep(64);
             t = *(volatile const uint32_t *)&src->tag;
         }
@@ -98,9 +119,10 @@ __device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer
 
 // Block-level reduction of the per-thread accumulators, then the "last block" publishes GVT (and, in a multi-GPU run
 // with fused exchange, does the cross-GPU round itself: no separate kernel between two super-steps).
-__device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t step, uint32_t world, uint32_t rank,
-                                             GvtSlot *const *peer_slots, bool fused)
+template <class M>
+__device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, uint32_t step)
 {
+    Ctl *ctl = d.ctl;
     __shared__ unsigned long long s_pend[kBlock / 32], s_emit[kBlock / 32];
     __shared__ unsigned int s_cnt[C_COUNT];
     __shared__ unsigned int s_last;
@@ -141,7 +163,7 @@ __device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t 
             const unsigned long long em = *(volatile unsigned long long *)&ctl->emit_min;
             g = from_ordered(pm < em ? pm : em);
             ctl->gvt_local = g;
-            if (world == 1) { const double cap = *(volatile double *)&ctl->gvt_cap; ctl->gvt = g < cap ? g : cap; }   // otherwise the cross-GPU minimum follows
+            if (d.world == 1) { const double cap = *(volatile double *)&ctl->gvt_cap; ctl->gvt = g < cap ? g : cap; }   // otherwise the cross-GPU minimum follows
             ctl->pend_min = ordered_bits(pos_inf());
             ctl->emit_min = ordered_bits(pos_inf());
             ctl->step = step + 1; ctl->c_steps += 1;
@@ -149,9 +171,9 @@ __device__ __forceinline__ void block_finish(Ctl *ctl, const Acc &acc, uint32_t 
             __threadfence();
         }
         __syncwarp();
-        if (world > 1 && fused) {
+        if (d.world > 1 && d.fused_gvt) {
             g = __shfl_sync(0xffffffffu, g, 0);
-            gvt_exchange_warp(ctl, peer_slots, rank, world, step + 1u, g);
+            gvt_exchange_warp(ctl, d.peer_slots, d.stage_cnt, d.rank, d.world, step + 1u, g, d.peer_timeout_ns);
         }
     }
 }
@@ -161,22 +183,105 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
 {
     Ctl *ctl = d.ctl;
     const double gvt = *(volatile double *)&ctl->gvt;
-    if (*(volatile uint32_t *)&ctl->error) return;
-    if (!(gvt <= d.stop)) return;                 // GVT passed the stop time: the run is complete
+    if (!(gvt <= d.stop)) return;                 // GVT passed the stop time: the run is complete (same answer in every block)
     const uint32_t step = *(volatile uint32_t *)&ctl->step;
-    double wend = d.stop;
-    if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
     Acc acc; acc.init();
-    extern __shared__ uint4 tw_queue_smem[];             // per warp: work queue + held messages (tw_core.cuh, WorkQ)
-    WorkQ<M> q;
-    q.init(reinterpret_cast<char *>(tw_queue_smem) + (threadIdx.x >> 5) * WorkQ<M>::kWarpBytes);
-    // one warp = d.tiles consecutive tiles of 32 LPs; the work queue is carried from tile to tile
-    const uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
-    for (uint32_t t = 0; t < d.tiles; ++t)
-        lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
-    q.drain(d, acc, step & 1u);
-    if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
-    block_finish(ctl, acc, step, d.world, d.rank, d.peer_slots, d.fused_gvt != 0u);
+    // An error recorded by an EARLIER launch: nothing to do.  The error word can also be set by a block of THIS launch
+    // while later blocks are still being scheduled; those must still take their ticket in block_finish, or no block would
+    // be the last one and neither the step counter nor (multi-GPU) the abort tag would be published.
+    if (*(volatile uint32_t *)&ctl->error == 0u) {
+        double wend = d.stop;
+        if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
+        extern __shared__ uint4 tw_queue_smem[];             // per warp: work queue + held messages (tw_core.cuh, WorkQ)
+        WorkQ<M> q;
+        q.init(reinterpret_cast<char *>(tw_queue_smem) + (threadIdx.x >> 5) * WorkQ<M>::kWarpBytes);
+        // one warp = d.tiles consecutive tiles of 32 LPs; the work queue is carried from tile to tile
+        const uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
+        for (uint32_t t = 0; t < d.tiles; ++t)
+            lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+        q.drain(d, acc, step & 1u);
+        if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
+    }
+    block_finish<M>(d, acc, step);
+}
+
+// Multi-GPU, between two super-steps: route what the other GPUs staged for this partition during the previous step.
+// The counts were published with the GVT mailbox entries of that step (tag == current step number).
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_deliver(const __grid_constant__ Dev<M> d)
+{
+    Ctl *ctl = d.ctl;
+    if (*(volatile uint32_t *)&ctl->error) return;
+    const uint32_t step = *(volatile uint32_t *)&ctl->step;
+    const uint32_t par_prev = (step & 1u) ^ 1u;
+    const GvtSlot *mine = d.peer_slots[d.rank] + (step & 1u) * kMaxWorld;
+    uint32_t cnt[kMaxWorld]; uint32_t total = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < (uint32_t)kMaxWorld; ++r) {
+        uint32_t c = 0;
+        if (r < d.world && r != d.rank && *(volatile const uint32_t *)&mine[r].tag == step) c = *(volatile const uint32_t *)&mine[r].count;
+        if (c > d.stage_cap) c = d.stage_cap;         // the sender has flagged the overflow; never read past the ring
+        cnt[r] = c; total += c;
+    }
+    Acc acc; acc.init();
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
+        uint32_t j = i, src = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < (uint32_t)kMaxWorld; ++r) if (src == r && j >= cnt[r]) { j -= cnt[r]; src = r + 1; }
+        deliver_staged<M>(d, acc, par_prev, src, j);
+    }
+    if (acc.err) { if (atomicCAS(&ctl->error, 0u, acc.err) == 0u) ctl->err_lp = acc.err_lp; }
+}
+
+// Closed groups (M::kGroup LPs that only ever talk to each other: the replicas of MachRep1/2): the causal chain of such
+// a model is one message hop per super-step (delta = 1e-6 look-ahead), which as grid-wide launches costs a launch and a
+// full GPU's latency chain per hop.  Here a warp owns `gpw` whole groups (one lane = one LP) and iterates their
+// super-steps inside the kernel -- same lp_step, same rollback and annihilation machinery, messages through the same
+// inbox rings --, synchronised by __syncwarp only.  Every group advances under its OWN GVT (the minimum over its LPs:
+// nobody else can ever send to it), bounded by the external Time Server's value when one is attached.  A launch runs an
+// even number of rounds per warp, so the arrival parity of every inbox stays aligned with the engine's step counter.
+template <class M>
+__global__ void __launch_bounds__(32) k_run_groups(const __grid_constant__ Dev<M> d, uint32_t gpw, uint32_t max_rounds)
+{
+    Ctl *ctl = d.ctl;
+    if (*(volatile uint32_t *)&ctl->error) return;
+    constexpr uint32_t G = M::kGroup;
+    const uint32_t lane = threadIdx.x;
+    const double cap = *(volatile double *)&ctl->gvt_cap;
+    const uint32_t step0 = *(volatile uint32_t *)&ctl->step;
+    extern __shared__ uint4 tw_queue_smem[];
+    WorkQ<M> q; q.init(tw_queue_smem);
+    Acc acc; acc.init();
+    double graw; uint32_t rounds;
+    const bool mine = group_rounds<M>(d, acc, q, blockIdx.x * gpw, gpw, max_rounds, step0, cap, graw, rounds);
+    const uint32_t base_lane = lane - lane % G;
+    const uint32_t grp = blockIdx.x * gpw + lane / G;
+    if (mine && lane == base_lane) d.grp_gvt[grp] = ordered_bits(graw);
+    // totals: counters, the partition's local time = minimum over its groups, the round count of the slowest warp
+    const uint32_t vals[C_COUNT] = {acc.exec, acc.rb_events, acc.rollbacks, acc.strag, acc.anti, acc.annih,
+                                    acc.retry, acc.sent_local, acc.sent_remote, acc.fossil};
+#pragma unroll
+    for (int i = 0; i < C_COUNT; ++i) {
+        const unsigned int s = __reduce_add_sync(0xffffffffu, vals[i]);
+        if (lane == 0 && s) atomicAdd(&ctl->c_exec + i, (unsigned long long)s);
+    }
+    if (acc.err) { if (atomicCAS(&ctl->error, 0u, acc.err) == 0u) ctl->err_lp = acc.err_lp; }
+    const unsigned long long wm = warp_min_u64(ordered_bits(graw));
+    if (lane == 0) {
+        atomicMin(&ctl->pend_min, wm);
+        atomicMax(&ctl->c_rounds, (unsigned long long)rounds);
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&ctl->done_blocks, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const double g = from_ordered(*(volatile unsigned long long *)&ctl->pend_min);
+            ctl->gvt_local = g; ctl->gvt = g < cap ? g : cap;
+            ctl->pend_min = ordered_bits(pos_inf());
+            ctl->c_steps += *(volatile unsigned long long *)&ctl->c_rounds; ctl->c_rounds = 0;
+            ctl->done_blocks = 0;
+            __threadfence();
+        }
+    }
 }
 
 template <class M>
@@ -186,11 +291,21 @@ __global__ void __launch_bounds__(kBlock) k_route(const Dev<M> d, const tw_event
     const uint32_t step = ctl->step;
     const double gvt = ctl->gvt;
     Acc acc; acc.init();
+    uint32_t skipped = 0;
     for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) {
         const tw_event w = evs[i];
-        if (w.recv_ts < gvt) { acc.fail(TW_ERR_OUTDATED_MESSAGE, w.dst); continue; }
+        if (w.recv_ts < gvt) {
+            // "Received the outdated message" (Internal/Event.hs:370-374): skipped when dioAllowSkippingOutdatedMessage
+            const uint32_t owner = d.world > 1 ? w.dst / d.n_per : 0u;
+            if (d.flags & kFlagSkipOutdated) { if (owner == d.rank) skipped++; }
+            else acc.fail(TW_ERR_OUTDATED_MESSAGE, w.dst);
+            continue;
+        }
         route_event<M>(d, acc, (step & 1u) ^ 1u, w);
+        if (d.grp_gvt && w.dst >= d.lp_base && w.dst - d.lp_base < d.n_local)          // closed groups keep their own GVT
+            atomicMin(&d.grp_gvt[(w.dst - d.lp_base) / M::kGroup], ordered_bits(w.recv_ts));
     }
+    if (skipped) atomicAdd(&ctl->c_skipped, (unsigned long long)skipped);
     // fold the injected minimum into GVT: gvt = min(gvt, min recv_ts)
     __shared__ unsigned long long s_emit[kBlock / 32];
     unsigned long long e = warp_min_u64(ordered_bits(acc.emit_min));
@@ -203,14 +318,15 @@ __global__ void __launch_bounds__(kBlock) k_route(const Dev<M> d, const tw_event
     }
 }
 
-// The same exchange as a kernel of its own (TWB200_GVT_KERNEL=1: comparison with the fused form).
-__global__ void k_gvt_exchange(Ctl *ctl, GvtSlot *const *peer_slots_dev, uint32_t rank, uint32_t world)
+// The same exchange as a kernel of its own (TWB200_GVT_KERNEL=1: comparison with the fused form; also the mode to use
+// under ncu or compute-sanitizer, which serialise kernels and would make the fused wait time out).
+__global__ void k_gvt_exchange(Ctl *ctl, GvtSlot *const *peer_slots_dev, uint32_t *stage_cnt, uint32_t rank, uint32_t world,
+                               unsigned long long timeout_ns)
 {
     const uint32_t tag = *(volatile uint32_t *)&ctl->step;
-    gvt_exchange_warp(ctl, peer_slots_dev, rank, world, tag, *(volatile double *)&ctl->gvt_local);
+    gvt_exchange_warp(ctl, peer_slots_dev, stage_cnt, rank, world, tag, *(volatile double *)&ctl->gvt_local, timeout_ns);
 }
 
-// after k_route: gvt = min(gvt, injected minimum)   (single thread)
 // GlobalTimeMessage from an external Time Server (single thread): the bound moves, GVT follows up to the local minimum
 __global__ void k_set_gvt_cap(Ctl *ctl, double cap, uint32_t world)
 {
@@ -219,6 +335,7 @@ __global__ void k_set_gvt_cap(Ctl *ctl, double cap, uint32_t world)
     else if (cap < ctl->gvt) ctl->gvt = cap;         // multi-GPU: the next mailbox round raises it again
 }
 
+// after k_route: gvt = min(gvt, injected minimum)   (single thread)
 __global__ void k_fold_inject(Ctl *ctl)
 {
     const double m = from_ordered(ctl->emit_min);
@@ -233,20 +350,23 @@ __global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_ti
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
     if (l == 0) {
         // the step counter is never rewound: it tags the cross-GPU GVT mailboxes, and a tag must not repeat across runs
-        const uint32_t next_step = d.ctl->step + 2u;
+        const uint32_t next_step = (d.ctl->step + 2u) & ~1u;
         Ctl c; memset(&c, 0, sizeof c);
         c.step = next_step;
         c.gvt = start_time; c.gvt_local = start_time;
         c.gvt_cap = cap0;
         c.pend_min = ordered_bits(pos_inf()); c.emit_min = ordered_bits(pos_inf());
         *d.ctl = c;
+        for (uint32_t r = 0; r < (uint32_t)kMaxWorld; ++r) d.stage_cnt[r * kCntStride] = 0u;
     }
     if (l >= d.n_local) return;
-    LPHdr h; h.head = 0; h.nproc = 0; h.consumed = 0; h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
+    LPHdr h; h.head = 0; h.np_hp = 0; h.consumed = 0; h.rollbacks = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
     d.hdr[l] = h;
     LPIn in; in.word = 0;
     d.in[l] = in;
     d.state[l] = M::initial_state(d.mp, d.lp_base + l);
+    // a group's own GVT starts at "nothing known yet"; k_route / the first round lower it to the earliest message
+    if (d.grp_gvt && l % M::kGroup == 0) d.grp_gvt[l / M::kGroup] = ordered_bits(start_time);
 }
 
 // After a consistency error (unmatched anti-message, time order, outdated message): was a ring overflow the cause?  An
@@ -259,7 +379,7 @@ __global__ void __launch_bounds__(kBlock) k_diagnose_overflow(const Dev<M> d)
     if (l >= d.n_local) return;
     // the same conservative rule as the LP's own check: everything reserved so far against the head at the start of the
     // LP's last completed step (senders of that step may have raced with its fossil collection)
-    if (in_total(d.in[l].word) - d.hdr[l].head_prev > d.cap) { d.ctl->error = TW_ERR_QUEUE_OVERFLOW; d.ctl->err_lp = d.lp_base + l; }
+    if (in_total(d.in[l].word) - hdr_head_prev(d.hdr[l]) > d.cap) { d.ctl->error = TW_ERR_QUEUE_OVERFLOW; d.ctl->err_lp = d.lp_base + l; }
 }
 
 template <class M>
@@ -342,7 +462,42 @@ struct EngineBase {
     virtual int local_time(double *t) = 0;
     virtual int global_time_message(double t, int *accepted) = 0;
     virtual int attach_time_server(int on) = 0;
+    virtual int skipped_outdated(uint64_t *n) = 0;
+    // dioSimulationMonitoringAction: the callback runs on a worker thread of its own, never on the thread that launches
+    // the super-steps (a slow callback must not delay the launches: other GPUs wait for this one in their mailbox round)
     tw_monitor_fn monitor = nullptr; void *monitor_user = nullptr;
+    std::thread mon_thread; std::mutex mon_mu; std::condition_variable mon_cv;
+    std::deque<tw_monitor_state> mon_q; bool mon_quit = false, mon_busy = false;
+    void monitor_post(const tw_monitor_state &ms)
+    {
+        if (!monitor) return;
+        std::lock_guard<std::mutex> g(mon_mu);
+        if (!mon_thread.joinable()) mon_thread = std::thread([this] { monitor_loop(); });
+        mon_q.push_back(ms); mon_cv.notify_all();
+    }
+    void monitor_loop()
+    {
+        std::unique_lock<std::mutex> lk(mon_mu);
+        for (;;) {
+            mon_cv.wait(lk, [this] { return mon_quit || !mon_q.empty(); });
+            if (mon_q.empty()) { if (mon_quit) return; continue; }
+            const tw_monitor_state ms = mon_q.front(); mon_q.pop_front();
+            tw_monitor_fn fn = monitor; void *user = monitor_user;
+            mon_busy = true; lk.unlock();
+            if (fn) fn(&ms, user);
+            lk.lock(); mon_busy = false; mon_cv.notify_all();
+        }
+    }
+    void monitor_flush()          // tw_run returns only after every posted state has been delivered
+    {
+        std::unique_lock<std::mutex> lk(mon_mu);
+        mon_cv.wait(lk, [this] { return mon_q.empty() && !mon_busy; });
+    }
+    void monitor_stop()
+    {
+        { std::lock_guard<std::mutex> g(mon_mu); mon_quit = true; mon_cv.notify_all(); }
+        if (mon_thread.joinable()) mon_thread.join();
+    }
 };
 
 #define TW_CUDA(call)                                                                                   \
@@ -375,8 +530,8 @@ static const char *code_name(int c)
     case TW_ERR_DEADLOCK: return "Detected a deadlock when retrying the computations (GVT stalled)";
     case TW_ERR_TIME_ORDER: return "The time value is too small (pending event older than the LP clock)";
     case TW_ERR_BAD_DESTINATION: return "receiver id outside [0, n_lps)";
-    case TW_ERR_MODEL: return "model handler reached an impossible state";
-    case TW_ERR_OUTBOX_OVERFLOW: return "cross-GPU staging buffer full";
+    case TW_ERR_MODEL: return "a model declared as closed groups sent a message outside the sender's group";
+    case TW_ERR_OUTBOX_OVERFLOW: return "cross-GPU staging ring full (raise tw_params.outbox_capacity)";
     case TW_ERR_NOT_SUPPORTED: return "not supported";
     default: return "unknown error";
     }
@@ -401,6 +556,8 @@ struct Engine : EngineBase {
     bool external_time = false;           // GVT bounded by an external Time Server (tw_attach_time_server)
     void *meta = nullptr; size_t meta_bytes = 0, l2_window_bytes = 0, l2_persist_bytes = 0;
     GvtSlot *d_slots = nullptr; GvtSlot **d_peer_slots = nullptr;      // my GVT mailbox; device copy of the peer table
+    bool group_kernel = false; uint32_t gpw = 1, group_grid = 0;      // closed-group models: k_run_groups instead of k_step
+    int deliver_grid = 0;
 
     int init(const tw_params &p)
     {
@@ -409,6 +566,8 @@ struct Engine : EngineBase {
         uint32_t cap = p.queue_capacity ? p.queue_capacity : 128;
         if (cap & (cap - 1)) { err = "queue_capacity must be a power of two"; return TW_ERR_INVALID_ARG; }
         if (cap < 8) { err = "queue_capacity must be >= 8"; return TW_ERR_INVALID_ARG; }
+        // nproc, the head delta and the per-parity arrival counts are 16-bit fields (LPHdr, LPIn)
+        if (cap > kMaxCap) { err = "queue_capacity must be <= 32768"; return TW_ERR_INVALID_ARG; }
         uint32_t mb = p.max_events_per_step ? p.max_events_per_step : 8;
         if (mb > (uint32_t)kMaxBatch) mb = kMaxBatch;
         int ndev = 0;
@@ -431,6 +590,12 @@ struct Engine : EngineBase {
         d.stop = p.stop_time;
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);
+        d.flags = p.flags;
+        {
+            double ms = p.sync_timeout_ms ? (double)p.sync_timeout_ms : 20000.0;   // a peer that stays away this long is gone
+            if (const char *e = getenv("TWB200_PEER_TIMEOUT_MS")) { const double v = atof(e); if (v > 0.0) ms = v; }
+            d.peer_timeout_ns = (unsigned long long)(ms * 1e6);
+        }
         const size_t nl = d.n_local ? d.n_local : 1;
         TW_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         TW_CUDA(cudaEventCreate(&ev0)); TW_CUDA(cudaEventCreate(&ev1));
@@ -448,6 +613,22 @@ struct Engine : EngineBase {
         d.in = (LPIn *)meta; d.hdr = (LPHdr *)((char *)meta + off_hdr); d.state = (typename M::State *)((char *)meta + off_state);
         TW_CUDA(cudaMalloc(&d.ctl, sizeof(Ctl)));
         TW_CUDA(cudaMemset(d.ctl, 0, sizeof(Ctl)));
+        TW_CUDA(cudaMalloc(&d.stage_cnt, kMaxWorld * kCntStride * sizeof(uint32_t)));
+        TW_CUDA(cudaMemset(d.stage_cnt, 0, kMaxWorld * kCntStride * sizeof(uint32_t)));
+        // Closed groups (replicas): a warp iterates the super-steps of its groups inside one launch (k_run_groups).  As many
+        // warps as the GPU keeps resident, each with as few groups as that allows: a round costs one latency chain however
+        // many lanes are busy.
+        if constexpr (M::kGroup > 1) if (!(p.flags & kFlagNoGroupKernel) && !getenv("TWB200_NO_GROUP_KERNEL")) {
+            group_kernel = true;
+            const uint32_t n_groups = d.n_local / M::kGroup;
+            const uint32_t resident = (uint32_t)prop.multiProcessorCount * 16u;
+            gpw = (n_groups + resident - 1) / resident; if (gpw < 1) gpw = 1;
+            const uint32_t max_gpw = 32u / M::kGroup; if (gpw > max_gpw) gpw = max_gpw;
+            if (const char *e = getenv("TWB200_GROUPS_PER_WARP")) { const long v = atol(e); if (v >= 1 && v <= (long)max_gpw) gpw = (uint32_t)v; }
+            group_grid = (n_groups + gpw - 1) / gpw; if (group_grid < 1) group_grid = 1;
+            TW_CUDA(cudaMalloc(&d.grp_gvt, (size_t)(n_groups ? n_groups : 1) * sizeof(unsigned long long)));
+            TW_CUDA(cudaFuncSetAttribute(k_run_groups<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WorkQ<M>::kWarpBytes));
+        }
         TW_CUDA(cudaMalloc(&d_tmp, 2 * sizeof(unsigned long long)));
         TW_CUDA(cudaHostAlloc(&h_ctl, 2 * sizeof(Ctl), cudaHostAllocDefault));
         grid = (int)((nl + kBlock - 1) / kBlock);
@@ -481,9 +662,8 @@ struct Engine : EngineBase {
                 l2_window_bytes = want; l2_persist_bytes = persist;
             }
         }
-        d.peer_pages[d.rank] = d.pages; d.peer_in[d.rank] = d.in;
-        // multi-GPU GVT: fused into k_step's last block unless a comparison mode is requested
-        d.fused_gvt = (p.world > 1 && !getenv("TWB200_GVT_KERNEL") && !getenv("TWB200_NCCL_GVT")) ? 1u : 0u;
+        // multi-GPU GVT: fused into k_step's last block unless the separate-kernel mode is requested (ncu, compute-sanitizer)
+        d.fused_gvt = (p.world > 1 && !getenv("TWB200_GVT_KERNEL")) ? 1u : 0u;
         if (p.world > 1) { int rc = init_peers(); if (rc) return rc; }
         return reset();
     }
@@ -491,15 +671,20 @@ struct Engine : EngineBase {
     // exchange cudaIpc handles of pages / inbox counters through NCCL and map every peer (NVLink P2P)
     static size_t stage_bytes() { return (size_t)(kBlock / 32) * WorkQ<M>::kWarpBytes; }   // work queues + held messages
 
+    // Map every peer's staging rings and GVT mailbox (cudaIpc handles exchanged through NCCL; NVLink P2P).
     int init_peers()
     {
         if (!g_nccl.load(err)) return TW_ERR_CUDA;
         NcclApi::Id128 id; memcpy(id.b, P.nccl_id, 128);
         TW_NCCL(g_nccl.CommInitRank(&comm, (int)P.world, id, (int)P.rank));
-        struct Handles { cudaIpcMemHandle_t pages, in, slots; };
+        // staging rings for what the other GPUs send here: [sender][parity][stage_cap] records.  Default capacity: two
+        // records per local LP and sender (a first super-step that executes a whole window at once fits).
+        d.stage_cap = P.outbox_capacity ? P.outbox_capacity : (d.n_per * 2u > 8192u ? d.n_per * 2u : 8192u);
+        const size_t ring_bytes = (size_t)P.world * 2u * d.stage_cap * sizeof(typename M::Event);
+        TW_CUDA(cudaMalloc(&d.stage_in, ring_bytes));
+        struct Handles { cudaIpcMemHandle_t stage, slots; };
         Handles mine; Handles *d_all = nullptr;
-        TW_CUDA(cudaIpcGetMemHandle(&mine.pages, d.pages));
-        TW_CUDA(cudaIpcGetMemHandle(&mine.in, d.in));
+        TW_CUDA(cudaIpcGetMemHandle(&mine.stage, d.stage_in));
         TW_CUDA(cudaMalloc(&d_slots, 2 * kMaxWorld * sizeof(GvtSlot)));
         TW_CUDA(cudaMemset(d_slots, 0xFE, 2 * kMaxWorld * sizeof(GvtSlot)));
         TW_CUDA(cudaIpcGetMemHandle(&mine.slots, d_slots));
@@ -513,15 +698,16 @@ struct Engine : EngineBase {
         TW_CUDA(cudaFree(d_all));
         for (uint32_t r = 0; r < P.world; ++r) {
             if (r == P.rank) continue;
-            void *pp = nullptr, *pi = nullptr, *ps = nullptr;
-            TW_CUDA(cudaIpcOpenMemHandle(&pp, all[r].pages, cudaIpcMemLazyEnablePeerAccess));
-            TW_CUDA(cudaIpcOpenMemHandle(&pi, all[r].in, cudaIpcMemLazyEnablePeerAccess));
+            void *pst = nullptr, *ps = nullptr;
+            TW_CUDA(cudaIpcOpenMemHandle(&pst, all[r].stage, cudaIpcMemLazyEnablePeerAccess));
             TW_CUDA(cudaIpcOpenMemHandle(&ps, all[r].slots, cudaIpcMemLazyEnablePeerAccess));
-            peer_ptrs.push_back(pp); peer_ptrs.push_back(pi); peer_ptrs.push_back(ps);
-            d.peer_pages[r] = (typename M::Event *)pp; d.peer_in[r] = (LPIn *)pi; d.peer_slots[r] = (GvtSlot *)ps;
+            peer_ptrs.push_back(pst); peer_ptrs.push_back(ps);
+            d.stage_out[r] = (typename M::Event *)pst + (size_t)P.rank * 2u * d.stage_cap;    // rank r's rings for sender `rank`
+            d.peer_slots[r] = (GvtSlot *)ps;
         }
         TW_CUDA(cudaMalloc(&d_peer_slots, kMaxWorld * sizeof(GvtSlot *)));
         TW_CUDA(cudaMemcpy(d_peer_slots, d.peer_slots, kMaxWorld * sizeof(GvtSlot *), cudaMemcpyHostToDevice));
+        deliver_grid = 148 * 4;
         // one rank per GPU: the mailbox exchange spins on peers, two ranks sharing a GPU could starve each other
         {
             int dev = 0; cudaGetDevice(&dev);
@@ -544,6 +730,15 @@ struct Engine : EngineBase {
         if (P.world <= 1) return TW_OK;
         // one-double all-reduce doubles as the cross-GPU barrier
         TW_NCCL(g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream));
+        return TW_OK;
+    }
+
+    int rendezvous()                     // cross-GPU barrier that leaves the control block alone
+    {
+        if (P.world <= 1) return TW_OK;
+        double *scratch = reinterpret_cast<double *>(d_tmp);
+        TW_NCCL(g_nccl.AllReduce(scratch, scratch + 1, 1, kNcclFloat64, kNcclMin, comm, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
         return TW_OK;
     }
 
@@ -606,20 +801,47 @@ struct Engine : EngineBase {
         cudaGraph_t g = nullptr;
         TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         for (uint32_t i = 0; i < steps; ++i) {
+            if (P.world > 1) k_deliver<M><<<deliver_grid, kBlock, 0, stream>>>(d);        // what the peers staged in the last step
             k_step<M><<<step_grid, kBlock, stage_bytes(), stream>>>(d);
-            if (P.world > 1 && !d.fused_gvt) {
-                if (getenv("TWB200_NCCL_GVT")) {         // fallback / comparison: ncclAllReduce(min) per super-step
-                    int e = g_nccl.AllReduce(&d.ctl->gvt_local, &d.ctl->gvt, 1, kNcclFloat64, kNcclMin, comm, stream);
-                    if (e) { cudaStreamEndCapture(stream, &g); if (g) cudaGraphDestroy(g); err = "ncclAllReduce failed during capture"; return TW_ERR_CUDA; }
-                } else {
-                    k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.rank, d.world);
-                }
-            }
+            if (P.world > 1 && !d.fused_gvt) k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.stage_cnt, d.rank, d.world, d.peer_timeout_ns);
         }
         TW_CUDA(cudaStreamEndCapture(stream, &g));
         TW_CUDA(cudaGraphInstantiate(&graph, g, 0));
         TW_CUDA(cudaGraphDestroy(g));
         graph_steps = steps; graph_stop = d.stop;
+        return TW_OK;
+    }
+    uint64_t launches_per_graph(uint32_t B) const { return P.world > 1 ? (d.fused_gvt ? 2ull * B : 3ull * B) : B; }
+
+    void post_monitor(const Ctl &c)
+    {
+        if (!monitor) return;
+        tw_monitor_state ms; memset(&ms, 0, sizeof ms);
+        ms.gvt = c.gvt; ms.steps = c.c_steps; ms.executed = c.c_exec; ms.rolled_back = c.c_rb_events;
+        ms.rollbacks = c.c_rollbacks; ms.anti_sent = c.c_anti; ms.annihilated = c.c_annih;
+        ms.sent_local = c.c_sent_local; ms.sent_remote = c.c_sent_remote; ms.n_lps_local = d.n_local; ms.rank = d.rank;
+        monitor_post(ms);
+    }
+
+    // closed-group models: every launch of k_run_groups advances all groups by up to `rounds` super-steps of their own
+    int run_groups(double until, const Ctl &c0, Ctl &last, bool &finished)
+    {
+        Dev<M> dg = d; dg.closed = 1u;
+        const uint32_t rounds = (P.steps_per_launch ? P.steps_per_launch : 16) * 64u;     // even
+        double last_gvt = c0.gvt; uint64_t stall = 0;
+        while (!finished) {
+            k_run_groups<M><<<group_grid, 32, WorkQ<M>::kWarpBytes, stream>>>(dg, gpw, rounds); count(1);
+            TW_CUDA(cudaGetLastError());
+            TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+            TW_CUDA(cudaStreamSynchronize(stream));
+            last = h_ctl[0];
+            post_monitor(last);
+            int rc = check_device_error(last); if (rc) return rc;
+            if (!(last.gvt <= until)) { finished = true; break; }
+            if (external_time && !(last.gvt < last.gvt_cap)) break;           // waiting for the next GlobalTimeMessage
+            if (last.gvt == last_gvt) { if (++stall > 64) { err = code_name(TW_ERR_DEADLOCK); return TW_ERR_DEADLOCK; } }
+            else { stall = 0; last_gvt = last.gvt; }
+        }
         return TW_OK;
     }
 
@@ -628,7 +850,10 @@ struct Engine : EngineBase {
         if (!(until <= P.stop_time)) until = P.stop_time;
         d.stop = until;
         const uint32_t B = P.steps_per_launch ? P.steps_per_launch : 16;
-        int rc = build_graph(B); if (rc) return rc;
+        if (!group_kernel) { int rc = build_graph(B); if (rc) return rc; }
+        // the ranks enter their first super-step together: the in-kernel mailbox wait of a rank that started early must
+        // not run into its timeout because a peer is still instantiating its graph
+        if (P.world > 1) { int rc = rendezvous(); if (rc) return rc; }
         Ctl c0;
         TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
         TW_CUDA(cudaStreamSynchronize(stream));
@@ -639,8 +864,9 @@ struct Engine : EngineBase {
         int slot = 0; bool pending[2] = {false, false};
         double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
         Ctl last = c0;
-        while (!finished) {
-            TW_CUDA(cudaGraphLaunch(graph, stream)); count((P.world > 1 && !d.fused_gvt) ? 2 * B : B);
+        if (group_kernel) { if constexpr (M::kGroup > 1) result = run_groups(until, c0, last, finished); }
+        else while (!finished) {
+            TW_CUDA(cudaGraphLaunch(graph, stream)); count(launches_per_graph(B));
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             TW_CUDA(cudaEventRecord(ev_chk[slot], stream));
             pending[slot] = true;
@@ -649,13 +875,7 @@ struct Engine : EngineBase {
                 TW_CUDA(cudaEventSynchronize(ev_chk[other]));
                 pending[other] = false;
                 last = h_ctl[other];
-                if (monitor) {
-                    tw_monitor_state ms; memset(&ms, 0, sizeof ms);
-                    ms.gvt = last.gvt; ms.steps = last.c_steps; ms.executed = last.c_exec; ms.rolled_back = last.c_rb_events;
-                    ms.rollbacks = last.c_rollbacks; ms.anti_sent = last.c_anti; ms.annihilated = last.c_annih;
-                    ms.sent_local = last.c_sent_local; ms.sent_remote = last.c_sent_remote; ms.n_lps_local = d.n_local; ms.rank = d.rank;
-                    monitor(&ms, monitor_user);
-                }
+                post_monitor(last);
                 if ((result = check_device_error(last)) != TW_OK) break;
                 if (!(last.gvt <= until)) { finished = true; break; }
                 if (external_time && !(last.gvt < last.gvt_cap)) break;       // waiting for the next GlobalTimeMessage
@@ -681,6 +901,7 @@ struct Engine : EngineBase {
         TW_CUDA(cudaStreamSynchronize(stream));
         const Ctl &c = h_ctl[0];
         if (result == TW_OK) result = check_device_error(c);
+        if (monitor) monitor_flush();
         if (st) {
             memset(st, 0, sizeof *st);
             st->gvt = c.gvt; st->device_ms = ms; st->steps = c.c_steps - c0.c_steps;
@@ -714,9 +935,10 @@ struct Engine : EngineBase {
         TW_CUDA(cudaStreamSynchronize(stream));
         memset(out, 0, sizeof *out);
         out->lp = lp; out->local_time = h.lvt; out->event_queue_time = h.min_pend;
-        out->event_queue_size = in_total(in.word) - h.head - h.nproc;
-        out->log_size = h.nproc; out->input_message_count = in_total(in.word) - h.head; out->output_message_count = h.nproc;
-        out->rollback_count = h_ctl[0].c_rollbacks; out->executed = s.n_exec; out->trace_hash = s.hash;
+        const uint32_t nproc = hdr_nproc(h);
+        out->event_queue_size = in_total(in.word) - h.head - nproc;
+        out->log_size = nproc; out->input_message_count = in_total(in.word) - h.head; out->output_message_count = nproc;
+        out->rollback_count = h.rollbacks; out->executed = s.n_exec; out->trace_hash = s.hash;
         return TW_OK;
     }
 
@@ -763,15 +985,24 @@ struct Engine : EngineBase {
         return TW_OK;
     }
     int attach_time_server(int on) override { external_time = on != 0; return reset(); }
+    int skipped_outdated(uint64_t *n) override
+    {
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        *n = h_ctl[0].c_skipped;
+        return TW_OK;
+    }
 
     ~Engine() override
     {
+        monitor_stop();
         if (stream) cudaStreamSynchronize(stream);
         if (graph) cudaGraphExecDestroy(graph);
         for (void *p : peer_ptrs) cudaIpcCloseMemHandle(p);
         if (comm) g_nccl.CommDestroy(comm);
         cudaFree(d.pages); cudaFree(d.saved); cudaFree(meta); cudaFree(d.ctl);
         cudaFree(d_stage); cudaFree(d_tmp); cudaFree(d_stats); cudaFree(d_slots); cudaFree(d_peer_slots);
+        cudaFree(d.stage_cnt); cudaFree(d.stage_in); cudaFree(d.grp_gvt);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
         if (ev_chk[0]) cudaEventDestroy(ev_chk[0]); if (ev_chk[1]) cudaEventDestroy(ev_chk[1]);
@@ -852,7 +1083,14 @@ int tw_gvt(tw_engine *e, double *g) { return (e && g) ? e->impl->gvt(g) : TW_ERR
 int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out) { return (e && out) ? e->impl->lp_state(lp, out) : TW_ERR_INVALID_ARG; }
 int tw_read_lp_stats(tw_engine *e, uint64_t *n_exec, uint64_t *hash, size_t n) { return (e && n_exec && hash) ? e->impl->read_lp_stats(n_exec, hash, n) : TW_ERR_INVALID_ARG; }
 int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n) { return (e && out) ? e->impl->read_machrep(out, n) : TW_ERR_INVALID_ARG; }
-int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user) { if (!e) return TW_ERR_INVALID_ARG; e->impl->monitor = fn; e->impl->monitor_user = user; return TW_OK; }
+int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user)
+{
+    if (!e) return TW_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(e->impl->mon_mu);
+    e->impl->monitor = fn; e->impl->monitor_user = user;
+    return TW_OK;
+}
+int tw_skipped_outdated(tw_engine *e, uint64_t *n) { return (e && n) ? e->impl->skipped_outdated(n) : TW_ERR_INVALID_ARG; }
 int tw_attach_time_server(tw_engine *e, int on) { return e ? e->impl->attach_time_server(on) : TW_ERR_INVALID_ARG; }
 int tw_local_time(tw_engine *e, double *t) { return (e && t) ? e->impl->local_time(t) : TW_ERR_INVALID_ARG; }
 int tw_global_time_message(tw_engine *e, double t, int *accepted) { return e ? e->impl->global_time_message(t, accepted) : TW_ERR_INVALID_ARG; }
@@ -885,7 +1123,7 @@ int tw_nccl_unique_id(uint8_t out[128])
 
 const char *tw_last_error(const tw_engine *e) { return e ? e->impl->err.c_str() : g_create_err.c_str(); }
 const char *tw_strerror(int code) { return code_name(code); }
-const char *tw_version(void) { return "twb200 0.1 sm_100a"; }
+const char *tw_version(void) { return "twb200 0.2 sm_100a"; }
 uint64_t tw_kernel_launch_count(void) { return g_launches.load(); }
 
 }  // extern "C"

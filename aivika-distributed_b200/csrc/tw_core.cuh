@@ -52,12 +52,23 @@
 
 namespace twb {
 
+// Inbox words are touched by the owning GPU only (messages from other GPUs arrive through the staging rings and are
+// routed by the owner, see StageOut / k_deliver): device scope is the right scope for them.
 #if defined(__CUDA_ARCH__)
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+TW_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+TW_HD void atomic_min_u64(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
 #elif defined(TW_SIMT_EMU)
+TW_HD void atomic_min_u64(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+}
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+TW_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 #else
 TW_HD unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+TW_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 #endif
 
 constexpr int kMaxBatch = 64;     // upper bound of events one LP executes per super-step (tw_params.max_events_per_step)
@@ -87,12 +98,17 @@ TW_HD double   from_ordered(uint64_t o) { return bits2d((o >> 63) ? (o & 0x7FFFF
 
 struct alignas(32) LPHdr {       // 32 B, owner-private
     uint32_t head;               // monotone index of the oldest retained entry
-    uint32_t nproc;              // processed entries: [head, head+nproc)
+    uint32_t np_hp;              // bits 0..15: processed entries [head, head+nproc); bits 16..31: head - head_prev, where
+                                 // head_prev = head at the start of the previous step (conservative overflow check)
     uint32_t consumed;           // entries [head, consumed) are known to the owner
-    uint32_t head_prev;          // head at the start of the previous step (conservative overflow check)
+    uint32_t rollbacks;          // rollback episodes of this LP (lpStateRollbackCount, Optimistic/State.hs:50)
     double   lvt;                // receive time of the last processed entry (queueTime), -inf if none
     double   min_pend;           // exact min receive time over pending entries, +inf if none
 };
+constexpr uint32_t kMaxCap = 32768;          // ring capacity bound: nproc and the head delta fit 16 bits, arrival counts too
+TW_HD uint32_t hdr_nproc(const LPHdr &h) { return h.np_hp & 0xFFFFu; }
+TW_HD uint32_t hdr_head_prev(const LPHdr &h) { return h.head - (h.np_hp >> 16); }
+TW_HD uint32_t hdr_pack(uint32_t nproc, uint32_t head, uint32_t head_prev) { return nproc | ((head - head_prev) << 16); }
 // Inbox word of an LP, touched by senders with ONE 64-bit atomic per message:
 //   bits 32..63  total : monotone slot-reservation counter (wraps harmlessly)
 //   bits  0..15  cnt0  : arrivals during even super-steps      bits 16..31  cnt1 : during odd super-steps
@@ -102,9 +118,18 @@ struct alignas(8) LPIn { unsigned long long word; };
 TW_HD uint32_t in_total(unsigned long long w) { return (uint32_t)(w >> 32); }
 TW_HD uint32_t in_count(unsigned long long w, uint32_t parity) { return (uint32_t)(w >> (16u * parity)) & 0xFFFFu; }
 TW_HD unsigned long long in_add(uint32_t parity) { return (1ull << 32) | (1ull << (16u * parity)); }
+TW_HD unsigned long long load_inbox_word(const LPIn *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldcg(&p->word);                 // L2 is where the atomics happen
+#else
+    return *(const volatile unsigned long long *)&p->word;
+#endif
+}
 
 // Cross-GPU GVT mailbox entry (peer-written over NVLink): value first, system fence, then the tag (= step number).
-struct alignas(16) GvtSlot { double value; uint32_t tag; uint32_t pad; };
+// `count` = messages the sender staged for this receiver during the step (StageOut): the receiver routes exactly that many.
+struct alignas(16) GvtSlot { double value; uint32_t tag; uint32_t count; };
 constexpr uint32_t kSlotEmpty = 0xFFFFFFFEu, kSlotAbort = 0xFFFFFFFFu;
 
 struct Ctl {                     // device-resident control block
@@ -117,6 +142,8 @@ struct Ctl {                     // device-resident control block
     unsigned long long c_exec, c_rb_events, c_rollbacks, c_strag, c_anti, c_annih, c_retry,
                        c_sent_local, c_sent_remote, c_fossil, c_steps;   // order == enum in engine.cu
     double   gvt_cap;            // GlobalTimeMessage of an external Time Server: gvt never exceeds it (+inf = none)
+    unsigned long long c_skipped; // host-injected messages older than GVT that were skipped (dioAllowSkippingOutdatedMessage)
+    unsigned long long c_rounds;  // closed-group kernel: rounds of the slowest warp, summed over launches
 };
 
 // per-thread accumulators, reduced per block by the kernel wrapper
@@ -140,6 +167,10 @@ struct Acc {
     }
 };
 
+constexpr uint32_t kCntStride = 32;          // staging counters sit 128 bytes apart (one L2 line each: no false contention)
+constexpr uint32_t kFlagSkipOutdated = 1u;   // tw_params.flags bit 0: dioAllowSkippingOutdatedMessage (Internal/DIO.hs:96-98)
+constexpr uint32_t kFlagNoGroupKernel = 2u;  // tw_params.flags bit 1: run closed-group models through k_step as well
+
 template <class M>
 struct Dev {                     // passed to kernels by value
     typename M::Event *pages;
@@ -153,11 +184,19 @@ struct Dev {                     // passed to kernels by value
     uint32_t rank, world;
     uint32_t fused_gvt;          // multi-GPU: the last block of k_step runs the GVT mailbox exchange itself
     uint32_t tiles;              // tiles of 32 LPs one warp runs per super-step (large partitions: fewer, fuller queue flushes)
+    uint32_t flags;              // kFlag*
+    uint32_t closed;             // closed-group kernel: a message must stay inside the sender's group of M::kGroup LPs
     double   stop, horizon;      // horizon < 0: unbounded
     typename M::Params mp;
-    typename M::Event *peer_pages[kMaxWorld];   // peer-mapped (NVLink P2P) inbox pages / counters
-    LPIn              *peer_in[kMaxWorld];
+    // Cross-GPU exchange (StageOut below): messages for LPs of rank r are appended to a staging ring that lives in r's
+    // memory (one ring per sender and step parity), slots taken from a sender-local counter.
+    typename M::Event *stage_in;                // my incoming rings: [sender rank][parity][stage_cap]
+    typename M::Event *stage_out[kMaxWorld];    // peer-mapped (NVLink P2P): rank r's rings for messages from me, [parity][stage_cap]
+    uint32_t          *stage_cnt;               // sender-local slot counters, [rank r * kCntStride], reset every step
+    uint32_t           stage_cap;
     GvtSlot           *peer_slots[kMaxWorld];   // every rank's GVT mailbox: slots[parity][sender rank]
+    unsigned long long *grp_gvt;                // closed-group kernel: ordered bits of every group's own GVT
+    unsigned long long peer_timeout_ns;         // wall-clock bound of the cross-GPU mailbox wait (a lost peer becomes an error)
 };
 
 template <class E>
@@ -174,32 +213,54 @@ TW_HD bool same_message(const E &a, const E &b)     // Eq Message ignores the pa
     return a.src == b.src && ((a.ctr ^ b.ctr) & kCtrMask) == 0 && a.recv_ts == b.recv_ts && a.send_ts == b.send_ts;
 }
 
-// sendMessage (Internal/OutputMessageQueue.hs:65-78) + deliverMessage: scatter into the receiver's inbox.
-// Two halves so that the reservation round trip (a returning atomic; over NVLink when the receiver lives on another GPU)
-// can overlap other work: emit_reserve returns the receiver's ring and the reserved index, the record store follows.
+// sendMessage (Internal/OutputMessageQueue.hs:65-78) + deliverMessage (Internal/DIO.hs:605-614): the scatter.
+//   receiver on this GPU      one 64-bit atomic on the receiver's inbox word reserves the ring slot and counts the arrival
+//   receiver on another GPU   the record goes into the staging ring the receiver keeps for this sender (peer store over
+//                             NVLink); the slot comes from a counter in the SENDER's memory -- no atomic crosses NVLink,
+//                             and the warp's work queue reserves once per destination GPU and flush (warp-aggregated).
+//                             The receiver routes the ring into its inboxes before its next super-step (deliver_staged);
+//                             the count travels with the GVT mailbox entry (GvtSlot::count).
+// emit_classify checks the destination and returns the owning rank and the local index there.
 template <class M>
-TW_HD typename M::Event *emit_reserve(const Dev<M> &d, Acc &acc, uint32_t parity, uint32_t lp, const typename M::Event &ev, uint32_t &idx)
+TW_HD bool emit_classify(const Dev<M> &d, Acc &acc, uint32_t lp, const typename M::Event &ev, uint32_t &owner, uint32_t &l)
 {
     const uint32_t dst = ev.dst;
-    if (dst >= d.n_global) { acc.fail(TW_ERR_BAD_DESTINATION, lp); return nullptr; }
+    if (dst >= d.n_global) { acc.fail(TW_ERR_BAD_DESTINATION, lp); return false; }
+    if (ev.recv_ts < ev.send_ts) { acc.fail(TW_ERR_SEND_AFTER_RECV, lp); return false; }
+    if (d.closed && dst / M::kGroup != lp / M::kGroup) { acc.fail(TW_ERR_MODEL, lp); return false; }   // not a closed group
     acc.emit_min = dmin(acc.emit_min, ev.recv_ts);
-    LPIn *in = d.in; typename M::Event *pages = d.pages;
-    uint32_t l = dst - d.lp_base;
-    if (d.world > 1) {
-        const uint32_t owner = dst / d.n_per;
-        l = dst - owner * d.n_per;
-        if (owner != d.rank) { in = d.peer_in[owner]; pages = d.peer_pages[owner]; acc.sent_remote++; }
-        else acc.sent_local++;
-    } else acc.sent_local++;
-    idx = in_total(atomic_add_u64(&in[l].word, in_add(parity)));
-    return pages + (size_t)l * d.cap;
+    if (ev.ctr & kAntiBit) acc.anti++;
+    owner = d.rank; l = dst - d.lp_base;
+    if (d.world > 1) { owner = dst / d.n_per; l = dst - owner * d.n_per; }
+    if (owner != d.rank) acc.sent_remote++; else acc.sent_local++;
+    return true;
 }
+// scalar form (CPU emulation without warps, k_route-like callers): reserve and store at once
 template <class M>
 TW_HD void emit_event(const Dev<M> &d, Acc &acc, uint32_t parity, uint32_t lp, const typename M::Event &ev)
 {
-    uint32_t idx = 0;
-    typename M::Event *ring = emit_reserve<M>(d, acc, parity, lp, ev, idx);
-    if (ring) ring[idx & d.mask] = ev;
+    uint32_t owner, l;
+    if (!emit_classify<M>(d, acc, lp, ev, owner, l)) return;
+    if (owner == d.rank) {
+        const uint32_t idx = in_total(atomic_add_u64(&d.in[l].word, in_add(parity)));
+        d.pages[(size_t)l * d.cap + (idx & d.mask)] = ev;
+    } else {
+        const uint32_t idx = atomic_add_u32(&d.stage_cnt[owner * kCntStride], 1u);
+        if (idx >= d.stage_cap) { acc.fail(TW_ERR_OUTBOX_OVERFLOW, lp); return; }
+        d.stage_out[owner][(size_t)parity * d.stage_cap + idx] = ev;
+    }
+}
+// The receiving side of the exchange: entry j of the ring that rank `src` filled during the previous super-step
+// (parity par_prev) goes into the destination LP's inbox exactly as if a local sender had delivered it in that step.
+// It is already part of GVT (the sender counted it in its emit minimum).
+template <class M>
+TW_HD void deliver_staged(const Dev<M> &d, Acc &acc, uint32_t par_prev, uint32_t src, uint32_t j)
+{
+    const typename M::Event ev = d.stage_in[((size_t)src * 2u + par_prev) * d.stage_cap + j];
+    const uint32_t l = ev.dst - d.lp_base;
+    if (ev.dst < d.lp_base || l >= d.n_local) { acc.fail(TW_ERR_BAD_DESTINATION, ev.dst); return; }
+    const uint32_t idx = in_total(atomic_add_u64(&d.in[l].word, in_add(par_prev)));
+    d.pages[(size_t)l * d.cap + (idx & d.mask)] = ev;
 }
 
 // An inconsistency seen by an LP (time order, unmatched anti-message, outdated message) can be the consequence of a
@@ -253,11 +314,7 @@ TW_HD void run_work(const Dev<M> &d, Acc &acc, uint32_t parity, const typename M
     const uint32_t lp = M::work_lp(w);
 #pragma unroll
     for (int k = 0; k < M::kMaxSends; ++k)
-        if (k < n) {
-            if (out[k].recv_ts < out[k].send_ts) { acc.fail(TW_ERR_SEND_AFTER_RECV, lp); continue; }
-            if (out[k].ctr & kAntiBit) acc.anti++;
-            emit_event<M>(d, acc, parity, lp, out[k]);
-        }
+        if (k < n) emit_event<M>(d, acc, parity, lp, out[k]);
 }
 
 template <class M>
@@ -267,7 +324,8 @@ struct WorkQ {
     static constexpr int G = (int)(sizeof(Event) / 16);      // 16-byte granules of one event record
     static_assert(sizeof(Event) % 16 == 0, "event records are held in 16-byte granules");
     // shared memory of one warp: the queue, then the held events (lane-interleaved granules), then their ring pointers
-    static constexpr size_t kWarpBytes = kQueueSlots * sizeof(Work) + (size_t)M::kMaxSends * 32 * (sizeof(Event) + 8);
+    // + 32 x 8 bytes: the per-group minimum of the messages sent in a round (closed-group kernel)
+    static constexpr size_t kWarpBytes = kQueueSlots * sizeof(Work) + (size_t)M::kMaxSends * 32 * (sizeof(Event) + 8) + 32 * 8;
 #if TW_SIMT
     Work *buf;                       // this warp's ring of kQueueSlots items in shared memory
     uint32_t head, tail;             // warp-uniform monotone indices
@@ -275,9 +333,14 @@ struct WorkQ {
     // reservations are in flight; the record stores are issued at the next flush (or at drain), when the indices have
     // long arrived.  The warp therefore never waits for a reservation round trip.
     uint4 *hold;                     // this lane's granule 0 of held event 0
-    unsigned long long *hring;       // this lane's ring pointer of held event 0
+    unsigned long long *hring;       // this lane's ring pointer of held event 0 (bit 0 set: a staging ring of another GPU)
     uint32_t hmask;                  // bit k: held event k is valid
-    uint32_t hidx[M::kMaxSends];     // reserved ring indices (results of the atomics, possibly still in flight)
+    uint32_t hidx[M::kMaxSends];     // local receiver: the reserved ring index; staged: the base index of the lane's group
+                                     // (valid on the group's leader lane) -- results of atomics, possibly still in flight
+    uint32_t hgrp[M::kMaxSends];     // staged: leader lane of the group | rank of this lane's message in the group << 5
+    // Closed-group kernel: a work item runs on whichever lane is free, but the group's GVT needs the minimum over the
+    // messages sent by ITS LPs: gmin[g] (shared memory) collects it per group of the warp, l0 = the warp's first local LP.
+    unsigned long long *gmin; uint32_t l0;
     __device__ __forceinline__ void init(void *warp_smem)
     {
         buf = reinterpret_cast<Work *>(warp_smem); head = tail = 0; hmask = 0;
@@ -286,44 +349,78 @@ struct WorkQ {
         hring = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(warp_smem) + kQueueSlots * sizeof(Work)
                                                        + (size_t)M::kMaxSends * 32 * sizeof(Event)) + lane;
 #pragma unroll
-        for (int k = 0; k < M::kMaxSends; ++k) hidx[k] = 0;
+        for (int k = 0; k < M::kMaxSends; ++k) { hidx[k] = 0; hgrp[k] = lane; }
+        gmin = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(warp_smem) + kQueueSlots * sizeof(Work)
+                                                      + (size_t)M::kMaxSends * 32 * (sizeof(Event) + 8));
+        l0 = 0;
     }
-    __device__ __forceinline__ void complete(const Dev<M> &d)
+    // issue the record stores of the previous flush (all lanes of the warp call it)
+    __device__ __forceinline__ void complete(const Dev<M> &d, Acc &acc)
     {
 #pragma unroll
-        for (int k = 0; k < M::kMaxSends; ++k)
-            if (hmask & (1u << k)) {
+        for (int k = 0; k < M::kMaxSends; ++k) {
+            uint32_t idx = hidx[k];
+            const bool held = (hmask & (1u << k)) != 0u;
+            unsigned long long rp = held ? hring[k * 32] : 0ull;
+            if (d.world > 1) {                               // kernel-uniform: staged messages take their slot from the group's base
+                const uint32_t base = __shfl_sync(0xffffffffu, hidx[k], (int)(hgrp[k] & 31u));
+                if (rp & 1ull) idx = base + (hgrp[k] >> 5);
+            }
+            if (held) {
                 Event e; uint4 *w = reinterpret_cast<uint4 *>(&e);
 #pragma unroll
                 for (int g = 0; g < G; ++g) w[g] = hold[(k * G + g) * 32];
-                Event *ring = reinterpret_cast<Event *>(hring[k * 32]);
-                ring[hidx[k] & d.mask] = e;
+                if (rp & 1ull) {
+                    if (idx >= d.stage_cap) acc.fail(TW_ERR_OUTBOX_OVERFLOW, e.src);
+                    else reinterpret_cast<Event *>(rp & ~1ull)[idx] = e;
+                } else reinterpret_cast<Event *>(rp)[idx & d.mask] = e;
             }
+        }
         hmask = 0;
     }
     // run the first n (<= 32) queued items, one per lane
     __device__ __forceinline__ void run(const Dev<M> &d, Acc &acc, uint32_t parity, uint32_t n)
     {
         const uint32_t lane = threadIdx.x & 31u;
-        complete(d);                                         // the previous flush's messages
+        complete(d, acc);                                    // the previous flush's messages
+        Event out[M::kMaxSends]; int nn = 0; uint32_t lp = 0;
         if (lane < n) {
             const Work w = buf[(head + lane) & (kQueueSlots - 1)];
-            Event out[M::kMaxSends]; int nn = 0;
             M::emit(d.mp, w, out, nn);
-            const uint32_t lp = M::work_lp(w);
+            lp = M::work_lp(w);
+        }
 #pragma unroll
-            for (int k = 0; k < M::kMaxSends; ++k)
-                if (k < nn) {
-                    if (out[k].recv_ts < out[k].send_ts) { acc.fail(TW_ERR_SEND_AFTER_RECV, lp); continue; }
-                    if (out[k].ctr & kAntiBit) acc.anti++;
-                    Event *ring = emit_reserve<M>(d, acc, parity, lp, out[k], hidx[k]);
-                    if (!ring) continue;
-                    const uint4 *src = reinterpret_cast<const uint4 *>(&out[k]);
-#pragma unroll
-                    for (int g = 0; g < G; ++g) hold[(k * G + g) * 32] = src[g];
-                    hring[k * 32] = (unsigned long long)ring;
-                    hmask |= 1u << k;
+        for (int k = 0; k < M::kMaxSends; ++k) {
+            uint32_t owner = d.rank, l = 0;
+            bool valid = k < nn;
+            if (valid) valid = emit_classify<M>(d, acc, lp, out[k], owner, l);
+            if (valid && d.closed) atomic_min_u64(&gmin[(lp - d.lp_base - l0) / M::kGroup], ordered_bits(out[k].recv_ts));
+            const bool staged = valid && owner != d.rank;
+            unsigned long long rp = 0ull;
+            if (d.world > 1) {
+                // warp-aggregated reservation: the messages of this flush that go to the same GPU take consecutive slots of
+                // its staging ring from ONE atomic on the sender-local counter (issued by the group's first lane)
+                const unsigned grp = __match_any_sync(0xffffffffu, staged ? owner : 0xFFFFFFFFu);
+                if (staged) {
+                    const uint32_t leader = (uint32_t)__ffs((int)grp) - 1u;
+                    const uint32_t rk = (uint32_t)__popc(grp & ((1u << lane) - 1u));
+                    hgrp[k] = leader | (rk << 5);
+                    if (rk == 0u) hidx[k] = atomic_add_u32(&d.stage_cnt[owner * kCntStride], (uint32_t)__popc(grp));
+                    rp = (unsigned long long)(d.stage_out[owner] + (size_t)parity * d.stage_cap) | 1ull;
                 }
+            }
+            if (valid && !staged) {
+                hidx[k] = in_total(atomic_add_u64(&d.in[l].word, in_add(parity)));
+                hgrp[k] = lane;
+                rp = (unsigned long long)(d.pages + (size_t)l * d.cap);
+            }
+            if (valid) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(&out[k]);
+#pragma unroll
+                for (int g = 0; g < G; ++g) hold[(k * G + g) * 32] = src[g];
+                hring[k * 32] = rp;
+                hmask |= 1u << k;
+            }
         }
         head += n;
         __syncwarp();
@@ -341,7 +438,7 @@ struct WorkQ {
     __device__ __forceinline__ void drain(const Dev<M> &d, Acc &acc, uint32_t parity)
     {
         if (tail != head) run(d, acc, parity, tail - head);
-        complete(d);
+        complete(d, acc);
     }
 #else
     void init(void *) {}
@@ -503,27 +600,30 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     const uint32_t par_prev = parity ^ 1u;
     const uint32_t mask = d.mask;
     bool live = l < d.n_local;
-    LPHdr h; h.head = h.nproc = h.consumed = h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
+    LPHdr h; h.head = h.np_hp = h.consumed = h.rollbacks = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
     State st;
     uint32_t head, nproc, consumed0, consumed;
     uint32_t narr = 0;
-    if (live) { h = d.hdr[l]; narr = in_count(d.in[l].word, par_prev); }
+    // (the inbox word is read past L1: senders change it with atomics, which L1 does not see -- the closed-group kernel
+    // runs many super-steps in one launch)
+    if (live) { h = d.hdr[l]; narr = in_count(load_inbox_word(&d.in[l]), par_prev); }
+    uint32_t head_prev = hdr_head_prev(h);
 
     // idle LP: no arrivals and nothing pending inside the window -> only the GVT contribution
     if (live && narr == 0 && !(h.min_pend <= wend)) {
         acc.pend_min = dmin(acc.pend_min, h.min_pend);
-        if (h.head_prev != h.head) d.hdr[l].head_prev = h.head;
+        if (head_prev != h.head) d.hdr[l].np_hp = hdr_pack(hdr_nproc(h), h.head, h.head);
         live = false;
     }
 
     Event *pg = d.pages + (size_t)(live ? l : 0) * d.cap;
     State *sv = d.saved + (size_t)(live ? l : 0) * d.cap;
-    head = h.head; nproc = h.nproc;
+    head = h.head; nproc = hdr_nproc(h);
     consumed0 = h.consumed; consumed = consumed0 + narr;
     if (live) {
         if (narr) atomic_add_u64(&d.in[l].word, 0ull - ((unsigned long long)narr << (16u * par_prev)));   // consume them
-        if (consumed - h.head_prev > d.cap) { acc.fail(TW_ERR_QUEUE_OVERFLOW, lp); live = false; }
-        h.head_prev = head;
+        if (consumed - head_prev > d.cap) { acc.fail(TW_ERR_QUEUE_OVERFLOW, lp); live = false; }
+        head_prev = head;
     }
     if (live) st = d.state[l];
 
@@ -560,7 +660,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (!(ts[u] >= gvt)) { fail_checked<M>(d, acc, TW_ERR_OUTDATED_MESSAGE, l, h.head_prev); live = false; }
+                if (!(ts[u] >= gvt)) { fail_checked<M>(d, acc, TW_ERR_OUTDATED_MESSAGE, l, head_prev); live = false; }
                 if ((ct[u] & kAntiBit) || (nproc > 0 && !(ts[u] > h.lvt))) slow = true;
             }
             a0 += left < 4u ? left : 4u;
@@ -570,7 +670,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     uint32_t rb = nproc;                                         // processed position to roll back to (nproc = none)
     if (slow) {
         StepCtx<M> c;                                            // lives in local memory only on this rare path
-        c.lvt = h.lvt; c.head_prev = h.head_prev; c.head = head; c.nproc = nproc; c.consumed0 = consumed0; c.consumed = consumed; c.rb = nproc; c.live = live;
+        c.lvt = h.lvt; c.head_prev = head_prev; c.head = head; c.nproc = nproc; c.consumed0 = consumed0; c.consumed = consumed; c.rb = nproc; c.live = live;
         Acc sacc; sacc.init();                                   // separate accumulators: `acc` must stay in registers
         drain_slow<M>(d, sacc, c, l);
         acc.merge(sacc);
@@ -585,7 +685,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     {
         const uint32_t rend = live ? nproc : 0u;
         const uint32_t rlow = (live && rb < nproc) ? rb : rend;
-        if (rlow < rend) acc.rollbacks++;
+        if (rlow < rend) { acc.rollbacks++; h.rollbacks++; }
         if constexpr (M::kReversible) {
             // reverse computation, newest first: undoing entry r leaves the state before r, which is also what its
             // anti-messages are regenerated from
@@ -785,7 +885,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
                 const uint32_t pi = done;                    // relative index of the slot being filled
                 Event e = pg[(pbeg + bix) & mask];
                 const Event x = pg[(pbeg + pi) & mask];      // its current occupant (loaded together with e)
-                if (e.recv_ts < h.lvt) { fail_checked<M>(d, acc, TW_ERR_TIME_ORDER, l, h.head_prev); live = false; stopped = true; searched = true; }
+                if (e.recv_ts < h.lvt) { fail_checked<M>(d, acc, TW_ERR_TIME_ORDER, l, head_prev); live = false; stopped = true; searched = true; }
                 else {
                     const State before = st;
                     const bool noop = (e.ctr & (kAntiBit | kDeadBit)) != 0;
@@ -844,12 +944,75 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
 
     // ---- 6. write back, GVT contribution
     if (live) {
-        h.head = head; h.nproc = nproc; h.consumed = consumed; h.min_pend = rest_min;
+        h.head = head; h.np_hp = hdr_pack(nproc, head, head_prev); h.consumed = consumed; h.min_pend = rest_min;
         d.hdr[l] = h;
         d.state[l] = st;
         acc.pend_min = dmin(acc.pend_min, rest_min);
     }
 }
+
+#if TW_SIMT
+// The warp-local super-step loop of a closed-group model (k_run_groups in engine.cu; tests/emu runs the same function with
+// 32 host threads): the warp owns groups [g0, g0 + gpw) of M::kGroup LPs, one lane = one LP, and runs their super-steps back
+// to back, every group under its own GVT.  Returns whether this lane owns an LP; graw = the GVT of the lane's group at
+// the end (whatever the external bound `cap` says), rounds = super-steps run (always even: the arrival parity of the
+// inboxes stays aligned with the engine's step counter `step0`).
+template <class M>
+__device__ __forceinline__ bool group_rounds(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t g0, uint32_t gpw, uint32_t max_rounds,
+                                             uint32_t step0, double cap, double &graw_out, uint32_t &rounds_out)
+{
+    constexpr uint32_t G = M::kGroup;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_groups = d.n_local / G;
+    const uint32_t grp = g0 + lane / G;
+    const bool mine = lane < gpw * G && grp < n_groups;
+    const uint32_t l = mine ? g0 * G + lane : 0xFFFFFFFFu;
+    const uint32_t base_lane = lane - lane % G;                            // first lane of my group
+    double graw = mine ? from_ordered(d.grp_gvt[grp]) : pos_inf();         // the group's own minimum, whatever the bound says
+    uint32_t rounds = 0, stalled = 0;
+    q.l0 = g0 * G;
+    for (;;) {
+        const double gvt = graw < cap ? graw : cap;
+        if ((rounds & 1u) == 0u) {                                         // a launch ends after an even number of rounds
+            // a group beyond the stop time is done; one that sits at the Time Server's bound waits for the next
+            // GlobalTimeMessage (the host returns and comes back)
+            const bool active = mine && gvt <= d.stop && !(graw > cap);
+            if (!__any_sync(0xffffffffu, active) || rounds >= max_rounds) break;
+        }
+        double wend = d.stop;
+        if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
+        acc.pend_min = pos_inf(); acc.emit_min = pos_inf();
+        q.gmin[lane] = ~0ull;
+        __syncwarp();
+        const uint32_t step = step0 + rounds;
+        lp_step<M>(d, acc, q, l, gvt, wend, step);                        // every group of the warp takes part in every round
+        q.drain(d, acc, step & 1u);
+        __syncwarp();
+        // the group's GVT: minimum over its lanes of what stays pending, and over the messages its LPs sent
+        const unsigned long long m = ordered_bits(acc.pend_min);
+        unsigned long long gm = mine ? q.gmin[lane / G] : ~0ull;
+#pragma unroll
+        for (uint32_t k = 0; k < G; ++k) {
+            const unsigned long long t = __shfl_sync(0xffffffffu, m, (int)((base_lane + k) & 31u));
+            gm = t < gm ? t : gm;
+        }
+        ++rounds;
+        if (mine) {
+            const double g = from_ordered(gm);
+            // a group that does not move for a very long time awaits a rollback that never comes (Internal/Event.hs:809-812)
+            stalled = (g == graw && g <= d.stop && !(g > cap)) ? stalled + 1u : 0u;
+            if (stalled > 200000u) acc.fail(TW_ERR_DEADLOCK, d.lp_base + l);
+            graw = g;
+        }
+        if (__any_sync(0xffffffffu, acc.err != 0u)) break;
+    }
+    graw_out = graw; rounds_out = rounds;
+    return mine;
+}
+#else
+template <class M>   // host pass of nvcc / scalar emulation: never called
+inline bool group_rounds(const Dev<M> &, Acc &, WorkQ<M> &, uint32_t, uint32_t, uint32_t, uint32_t, double, double &g, uint32_t &r) { g = 0.0; r = 0; return false; }
+#endif
 
 // Host-injected / cross-GPU routed message -> destination inbox (thread per message).
 template <class M>

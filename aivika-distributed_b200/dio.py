@@ -32,21 +32,32 @@ class SimulationAbort(RuntimeError):
 # ---------------------------------------------------------------- parameters (reference field names)
 @dataclass
 class DIOParams:
+    """defaultDIOParams (Internal/DIO.hs:196-217); only the fields that touch the event-processing path are carried.
+
+    How the reference's thresholds act here (isEventOverflow, Internal/Event.hs:289-306, throttles optimism when the
+    undo log or the output queue of an LP grows past its threshold): an LP's undo log and output queue are its
+    processed-but-uncommitted entries, bounded by `procLimit` (default: a quarter of the ring); a threshold below that
+    lowers the bound (`make_params`).  There is no transient-message queue on the device (messages are delivered between
+    two super-steps, none is in flight at a GVT cut), so dioTransientMessageQueueSizeThreshold has nothing to bound.
+    dioSyncTimeout bounds how long a GPU waits for its peers' GVT mailbox entries (reference: the synchronisation
+    timeout of blocking operations, in microseconds)."""
     dioLoggingPriority: str = "WARNING"
     dioName: str = "LP"
     dioTimeHorizon: Optional[float] = None                  # Nothing = unbounded optimism
-    dioUndoableLogSizeThreshold: int = 10_000_000           # mapped onto the per-LP ring capacity
+    dioUndoableLogSizeThreshold: int = 10_000_000
     dioOutputMessageQueueSizeThreshold: int = 10_000
     dioTransientMessageQueueSizeThreshold: int = 5_000
     dioSyncTimeout: int = 60_000_000
-    dioAllowPrematureIO: bool = False
-    dioAllowSkippingOutdatedMessage: bool = False           # outdated messages are always an error here
+    dioAllowPrematureIO: bool = False                       # results are only read at GVT == stop: never premature
+    dioAllowSkippingOutdatedMessage: bool = True            # Internal/DIO.hs:206; False: TW_ERR_OUTDATED_MESSAGE
     # engine-specific knobs (no reference counterpart)
     queueCapacity: int = 128
     maxEventsPerStep: int = 4
     stepsPerLaunch: int = 16
     procLimit: int = 0
     fossilThreshold: int = 0
+    outboxCapacity: int = 0                                 # multi-GPU staging ring records (0 = engine default)
+    closedGroupKernel: bool = True                          # MachRep1/2: warp-local super-step loop (k_run_groups)
 
 
 defaultDIOParams = DIOParams()
@@ -177,7 +188,16 @@ def make_params(model, ps: DIOParams, specs: Specs, rank=0, world=1, device=-1, 
     model.fill(p)
     p.rank = rank; p.world = world; p.device = device
     p.queue_capacity = ps.queueCapacity; p.max_events_per_step = ps.maxEventsPerStep
-    p.steps_per_launch = ps.stepsPerLaunch; p.proc_limit = ps.procLimit; p.fossil_threshold = ps.fossilThreshold
+    p.steps_per_launch = ps.stepsPerLaunch; p.fossil_threshold = ps.fossilThreshold
+    # isEventOverflow: the undo log / output queue of an LP = its processed-but-uncommitted entries (<= 3 messages each)
+    sends = 1 if isinstance(model, PHOLD) else 3
+    limit = ps.procLimit if ps.procLimit else max(1, ps.queueCapacity // 4)
+    limit = min(limit, max(1, ps.dioUndoableLogSizeThreshold), max(1, ps.dioOutputMessageQueueSizeThreshold // sends))
+    p.proc_limit = 0 if (not ps.procLimit and limit == max(1, ps.queueCapacity // 4)) else limit
+    p.outbox_capacity = ps.outboxCapacity
+    p.sync_timeout_ms = max(1, min(ps.dioSyncTimeout // 1000, 0xFFFFFFFF))        # microseconds -> milliseconds
+    p.flags = (ffi.TW_FLAG_SKIP_OUTDATED if ps.dioAllowSkippingOutdatedMessage else 0) | \
+              (0 if ps.closedGroupKernel else ffi.TW_FLAG_NO_GROUP_KERNEL)
     p.start_time = specs.spcStartTime; p.stop_time = specs.spcStopTime
     p.time_horizon = -1.0 if ps.dioTimeHorizon is None else float(ps.dioTimeHorizon)
     if nccl_id is not None:
@@ -279,6 +299,12 @@ class DIO:
         t = C.c_double()
         self._check(self.lib.tw_local_time(self.h, C.byref(t)))
         return t.value
+
+    def skippedOutdatedMessages(self):
+        """Messages dropped because their receive time was below the global time (dioAllowSkippingOutdatedMessage)."""
+        n = C.c_uint64()
+        self._check(self.lib.tw_skipped_outdated(self.h, C.byref(n)))
+        return n.value
 
     def globalTimeMessage(self, t):
         """GlobalTimeMessage t -> updateGlobalTime; returns False when the value was ignored (above the local time)."""

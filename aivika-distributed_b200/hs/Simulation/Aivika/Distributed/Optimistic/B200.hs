@@ -60,7 +60,7 @@ data MachRepResult = MachRepResult { totalUpTime :: Double, nRep :: Int64, nImme
 
 -- sizes / offsets of the C structs (include/twb200.h; checked by tests/test_abi.py against gcc)
 sizeofParams, sizeofEvent, sizeofRunStats, sizeofMachRep :: Int
-sizeofParams = 288; sizeofEvent = 48; sizeofRunStats = 120; sizeofMachRep = 40
+sizeofParams = 296; sizeofEvent = 48; sizeofRunStats = 120; sizeofMachRep = 40
 
 foreign import ccall safe "tw_create"  c_tw_create  :: Ptr () -> Ptr (Ptr ()) -> IO CInt
 foreign import ccall safe "tw_destroy" c_tw_destroy :: Ptr () -> IO CInt
@@ -95,6 +95,7 @@ pokeParams p model B200Params{..} B200Specs{..} = do
   pokeByteOff p 32 spcStartTime
   pokeByteOff p 40 spcStopTime
   pokeByteOff p 48 (maybe (-1) id dioTimeHorizon :: Double)
+  pokeByteOff p 68 (1 :: Word32)            -- flags: TW_FLAG_SKIP_OUTDATED (dioAllowSkippingOutdatedMessage = True, Internal/DIO.hs:206)
   case model of
     ModelPHOLD{..} -> do
       pokeByteOff p 0 (1 :: Word32); pokeByteOff p 4 pholdLPs

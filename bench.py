@@ -25,22 +25,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-ALGO_BYTES_PHOLD = 208      # bytes per committed PHOLD event
-ALGO_BYTES_MACHREP = 288
-
-WORKLOADS = {
-    # name: (description, model kwargs, stop, default horizon, capacity, cpu-sample stop)
-    "c4": dict(desc="PHOLD 1M LPs, 50% remote, P=16, lookahead 0.1, exp(1) delays, T=20 (BASELINE configs[3])",
-               kind="phold", n_lps=1 << 20, remote_pct=50, stop=20.0, horizon=0.3, batch=6, cap=128, cpu_stop=0.5),
-    "c3": dict(desc="PHOLD 64K LPs, 10% remote, P=16, lookahead 0.1, exp(1) delays, T=100 (BASELINE configs[2])",
-               kind="phold", n_lps=1 << 16, remote_pct=10, stop=100.0, horizon=0.2, batch=6, cap=128, cpu_stop=10.0),
-    "c5": dict(desc="rollback-heavy PHOLD 256K LPs, 50% remote, 10% of the remote messages to 4096 hot LPs "
-                    "(each hot LP holds ~7x the average event population), T=20 (BASELINE configs[4])",
-               kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10, stop=20.0, horizon=0.3, batch=16, cap=512,
-               cpu_stop=2.0),
-    "c2": dict(desc="MachRep2DistributedReproducible replicated as 4096 independent 3-LP groups, stop 1000 (BASELINE configs[1])",
-               kind="machrep", n_replicas=4096, stop=1000.0, horizon=2.0, batch=4, cap=256, cpu_stop=1000.0),
-}
 
 
 def load_pkg():
@@ -54,6 +38,24 @@ def load_pkg():
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+pkg = load_pkg()
+from aivika_distributed_b200 import workloads as W  # noqa: E402
+
+WORKLOADS = W.WORKLOADS
+ALGO_BYTES_PHOLD, ALGO_BYTES_MACHREP = W.ALGO_BYTES_PHOLD, W.ALGO_BYTES_MACHREP
+
+
+def oracle_fixture(args, wl):
+    """The oracle's answer for this exact workload (tests/golden/full_configs.json, written by
+    tests/golden/make_golden_full.py), or None when the run departs from the benched configuration."""
+    if args.seed != W.SEED or args.stop is not None or args.n_lps is not None or args.remote_pct is not None:
+        return None
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "full_configs.json"))).get(args.workload)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -173,6 +175,8 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=16)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-group-kernel", action="store_true",
+                    help="diagnostic: run MachRep2 through grid-wide super-steps (k_step) instead of the closed-group kernel")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.stop is not None:
@@ -217,7 +221,8 @@ def main():
         model = D.MachRep2(n_replicas=wl["n_replicas"])
         algo_bytes = ALGO_BYTES_MACHREP
     ps = D.DIOParams(dioTimeHorizon=None if wl["horizon"] < 0 else wl["horizon"], queueCapacity=wl["cap"],
-                     maxEventsPerStep=args.batch, stepsPerLaunch=args.steps_per_launch)
+                     maxEventsPerStep=args.batch, stepsPerLaunch=args.steps_per_launch,
+                     closedGroupKernel=not args.no_group_kernel)
     specs = D.Specs(0.0, wl["stop"])
     dio = D.DIO(model, ps, specs, rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
 
@@ -240,7 +245,7 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    dev_ms, e2e_s, committed, hashes, stats = [], [], [], [], []
+    dev_ms, e2e_s, committed, hashes, stats, digests = [], [], [], [], [], []
     launches0 = None
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
@@ -258,20 +263,29 @@ def main():
             dev_ms.append(st.device_ms); e2e_s.append(t1 - t0); committed.append(int(st.committed))
             hashes.append(int(st.trace_hash_sum)); stats.append(st.as_dict())
             assert int(n_exec.sum()) == int(st.committed)
+            digests.append(W.lp_digest(dio.lp_base, n_exec, h))
     launches = lib.tw_kernel_launch_count() - launches0
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
-    assert len(set(committed)) == 1 and len(set(hashes)) == 1, "the committed trace must not depend on the run"
+    assert len(set(committed)) == 1 and len(set(hashes)) == 1 and len(set(digests)) == 1, "the committed trace must not depend on the run"
+    rep_digest = 0
+    if wl["kind"] == "machrep":
+        res = dio.machRepResults()
+        rep_digest = W.machrep_digest((dio.lp_base + 2) // 3, res)
 
     # max over ranks of the per-step device time, sum over ranks of the committed events
     ms_l, e2e_l, cnt = D.reduce_run(dist, world, dev_ms, e2e_s,
                                     [committed[0], stats[-1]["executed"], stats[-1]["rolled_back"], stats[-1]["anti_sent"],
                                      stats[-1]["sent_remote"], stats[-1]["sent_local"], launches,
-                                     hashes[0] & 0xFFFFFFFF, hashes[0] >> 32], device="cuda")
+                                     hashes[0] & 0xFFFFFFFF, hashes[0] >> 32, digests[0] & 0xFFFFFFFF, digests[0] >> 32,
+                                     rep_digest & 0xFFFFFFFF, rep_digest >> 32], device="cuda")
     total_ms = float(sum(ms_l)); total_e2e = float(sum(e2e_l))
-    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, h_lo, h_hi = cnt
-    trace_hash_total = ((h_hi << 32) + h_lo) & ((1 << 64) - 1)       # sum over all LPs of the box, mod 2^64
+    tot_committed, tot_exec, tot_rb, tot_anti, tot_remote, tot_local, tot_launch, h_lo, h_hi, d_lo, d_hi, r_lo, r_hi = cnt
+    M64 = (1 << 64) - 1
+    trace_hash_total = ((h_hi << 32) + h_lo) & M64                   # sum over all LPs of the box, mod 2^64
+    lp_digest_total = ((d_hi << 32) + d_lo) & M64
+    rep_digest_total = ((r_hi << 32) + r_lo) & M64
     K = args.steps
     value = tot_committed * K / (total_ms / 1e3)
     e2e_value = tot_committed * K / total_e2e
@@ -283,12 +297,33 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None        # DRAM bytes per k_step launch from the committed ncu --set full capture of this workload
+        # DRAM bytes per launch of the dominant kernel: only from an ncu --set full capture of THIS workload at THIS
+        # partition size (profiles/traffic.json, written by tools/profile_round.sh + tools/ncu_traffic.py); null otherwise
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:lps{dio.n_local}:world{world}")
+            if t and args.stop is None and args.n_lps is None and args.remote_pct is None:
+                traffic, traffic_src = t["dram_bytes_per_launch"], t.get("source")
         except Exception:
             pass
         steps_per_run = stats[-1]["steps"]
+        grouped = wl["kind"] == "machrep" and not args.no_group_kernel
+        kern = "k_run_groups<MachRepModel>" if grouped else ("k_step<PholdModel>" if wl["kind"] == "phold" else "k_step<MachRepModel>")
+        # launches of the dominant kernel in one run: one per super-step, or (closed-group kernel) a handful per run
+        n_launch = max(1, stats[-1]["kernel_launches"] - 2) if grouped else max(1, steps_per_run)
+        # parity with the CPU oracle at the benched size: committed count, trace-hash sum, LP-bound digest (+ MachRep2 results)
+        fx = oracle_fixture(args, wl)
+        if fx is None:
+            parity = {"checked": False, "why": "diagnostic override: not one of the pinned configurations"}
+        else:
+            parity = {"checked": True, "fixture": "tests/golden/full_configs.json (oracle/oracle.c, sequential ground truth)",
+                      "committed": tot_committed == fx["committed"], "trace_hash_sum": hex(trace_hash_total) == fx["trace_hash_sum"],
+                      "lp_digest": hex(lp_digest_total) == fx["lp_digest"]}
+            if wl["kind"] == "machrep":
+                parity["replica_digest"] = hex(rep_digest_total) == fx["replica_digest"]
+            bad = [k for k, v in parity.items() if v is False]
+            assert not bad, f"PARITY FAILURE against the oracle fixture for {args.workload}: {bad} " \
+                            f"(committed {tot_committed} vs {fx['committed']}, hash {hex(trace_hash_total)} vs {fx['trace_hash_sum']})"
         achieved = (tot_committed / world) * algo_bytes * K / (total_ms / 1e3) / 1e9
         line = {
             "metric": "committed events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": K,
@@ -302,19 +337,22 @@ def main():
             "rollback_efficiency": tot_committed / max(1, tot_exec),
             "rolled_back_per_step": tot_rb, "anti_messages_per_step": tot_anti,
             "remote_messages_per_step": tot_remote, "local_messages_per_step": tot_local,
-            "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(trace_hash_total),
+            "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(trace_hash_total), "lp_digest": hex(lp_digest_total),
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": tot_launch,
             "nvlink": None if world == 1 else {
                 "achieved_gbs_per_gpu": tot_remote * (32 if wl["kind"] == "phold" else 48) * K / (total_ms / 1e3) / 1e9 / world,
                 "peak_gbs_per_direction": 770.0,
-                "note": "32 B (PHOLD) / 48 B (MachRep2) per message whose destination LP lives on another GPU, written as "
-                        "peer stores from k_step; peak = measured peer copy (B200_PROFILING.md)"},
+                "note": "32 B (PHOLD) / 48 B (MachRep2) per message whose destination LP lives on another GPU, written as peer "
+                        "stores from k_step into the receiver's staging ring (no atomic crosses NVLink); algorithmic bytes / "
+                        "time, not a counter; peak = measured peer copy (B200_PROFILING.md)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic,
-                         "note": f"k_step: {algo_bytes} algorithmic B per committed event (SURVEY.md 8d) x "
-                                 f"{tot_committed / world / max(1, steps_per_run):.0f} events per launch, "
-                                 f"{total_ms / K / max(1, steps_per_run) * 1e3:.2f} us per launch; peak = measured copy bandwidth"
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kern,
+                         "note": f"{kern}: {algo_bytes} algorithmic B per committed event (SURVEY.md 8d) x "
+                                 f"{tot_committed / world / max(1, n_launch):.0f} events per launch, "
+                                 f"{total_ms / K / max(1, n_launch) * 1e3:.2f} us per launch; peak = measured copy bandwidth"
                                  + ("" if peaks else " (fallback)")},
             "clocks": sampler.summary(),
         }

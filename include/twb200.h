@@ -38,12 +38,21 @@ enum {
     TW_ERR_DEADLOCK           = 7,   /* "Detected a deadlock when retrying the computations" Internal/Event.hs:809-812 */
     TW_ERR_TIME_ORDER         = 8,   /* "The time value is too small" Internal/Event.hs:223-227 */
     TW_ERR_BAD_DESTINATION    = 9,   /* receiver id outside [0, n_lps) */
-    TW_ERR_MODEL              = 10,  /* model handler reached an impossible state at GVT */
-    TW_ERR_OUTBOX_OVERFLOW    = 11,  /* cross-GPU staging buffer full */
+    TW_ERR_MODEL              = 10,  /* a model registered as closed groups sent a message outside the sender's group */
+    TW_ERR_OUTBOX_OVERFLOW    = 11,  /* cross-GPU staging ring full: raise tw_params.outbox_capacity */
     TW_ERR_NOT_SUPPORTED      = 12
 };
 
 enum { TW_MODEL_PHOLD = 1, TW_MODEL_MACHREP2 = 2, TW_MODEL_MACHREP1 = 3 };
+
+/* tw_params.flags */
+enum {
+    TW_FLAG_SKIP_OUTDATED   = 1,     /* dioAllowSkippingOutdatedMessage (Internal/DIO.hs:96-98; reference default True, :206): a
+                                        host-injected message older than GVT is counted and dropped instead of raising
+                                        TW_ERR_OUTDATED_MESSAGE (Internal/Event.hs:370-374) */
+    TW_FLAG_NO_GROUP_KERNEL = 2      /* closed-group models (MachRep1/2): one grid-wide super-step per launch like PHOLD, instead
+                                        of the warp-local super-step loop (same results; for comparison and tests) */
+};
 
 /* MachRep2 message kinds == the message data types of tests/MachRep2DistributedReproducible.hs:88-104 */
 enum {
@@ -101,19 +110,25 @@ typedef struct tw_params {
     uint32_t n_lps;               /* global LP count (MachRep1/MachRep2: 3 * replicas) */
     uint32_t rank, world;         /* this partition / number of partitions (GPUs); LP i lives on i / ceil(n_lps/world) */
     int32_t  device;              /* CUDA device ordinal, -1 = current */
-    uint32_t queue_capacity;      /* per-LP slots (power of two); ~ dioUndoableLogSizeThreshold / dioOutputMessageQueueSizeThreshold */
+    uint32_t queue_capacity;      /* per-LP ring slots: a power of two, 8..32768 */
     uint32_t max_events_per_step; /* optimistic batch per LP per super-step, 1..64 (0 = 8) */
     uint32_t steps_per_launch;    /* super-steps per graph launch between host GVT checks */
     double   start_time;          /* spcStartTime */
     double   stop_time;           /* spcStopTime (inclusive, Internal/Event.hs:228-229) */
     double   time_horizon;        /* dioTimeHorizon; < 0 or NaN == Nothing (unbounded optimism) */
-    uint32_t proc_limit;          /* processed-but-uncommitted entries per LP before optimism stalls (0 = capacity/4) */
+    uint32_t proc_limit;          /* processed-but-uncommitted entries per LP before optimism stalls (0 = capacity/4): the
+                                     per-LP form of dioUndoableLogSizeThreshold / dioOutputMessageQueueSizeThreshold
+                                     (isEventOverflow, Internal/Event.hs:289-306) */
     uint32_t fossil_threshold;    /* lazy fossil collection trigger (0 = capacity/8) */
-    uint32_t outbox_capacity;     /* reserved (cross-GPU staging) */
-    uint32_t flags;               /* reserved */
+    uint32_t outbox_capacity;     /* multi-GPU: records per staging ring (one ring per sender GPU and step parity in the
+                                     receiver's memory); 0 = max(8192, 2 * LPs per GPU) */
+    uint32_t flags;               /* TW_FLAG_* */
     tw_phold_params   phold;
     tw_machrep_params machrep;
     uint8_t  nccl_id[128];        /* ncclUniqueId shared by all ranks when world > 1 (tw_nccl_unique_id) */
+    uint32_t sync_timeout_ms;     /* dioSyncTimeout (Internal/DIO.hs:88-89, default 60 s): how long a GPU waits for the GVT mailbox
+                                     entry of a peer before the run fails with TW_ERR_DEADLOCK; 0 = 20000 */
+    uint32_t reserved;
 } tw_params;
 
 /* Result of tw_run: counters the reference never kept next to its lpStateRollbackCount. */
@@ -143,7 +158,7 @@ typedef struct tw_lp_state {
     uint32_t log_size;                 /* lpStateLogSize (processed, uncommitted) */
     uint32_t input_message_count;      /* lpStateInputMessageCount */
     uint32_t output_message_count;     /* lpStateOutputMessageCount (regenerated by replay: processed entries) */
-    uint64_t rollback_count;           /* lpStateRollbackCount (engine-wide; per-LP not kept) */
+    uint64_t rollback_count;           /* lpStateRollbackCount: rollback episodes of this LP */
     uint64_t executed;                 /* committed handler executions of this LP */
     uint64_t trace_hash;
 } tw_lp_state;
@@ -188,8 +203,9 @@ int tw_read_machrep(tw_engine *e, tw_machrep_result *out, size_t n_replicas);
 
 /*
  * Monitoring: dioSimulationMonitoringAction (Internal/DIO.hs:453-476) + TimeServerState
- * (Optimistic/State.hs:57-68).  The callback runs on the calling thread every time tw_run inspects the device
- * control block (once per graph launch of steps_per_launch super-steps).
+ * (Optimistic/State.hs:57-68).  The callback is invoked once per inspection of the device control block (every
+ * steps_per_launch super-steps) on a worker thread owned by the engine -- never on the thread that launches the
+ * super-steps --, in order; tw_run returns after the last invocation has finished.
  */
 typedef struct tw_monitor_state {
     double   gvt;                 /* tsStateGlobalVirtualTime */
@@ -215,6 +231,9 @@ int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user);
 int tw_attach_time_server(tw_engine *e, int on);
 int tw_local_time(tw_engine *e, double *local_time);
 int tw_global_time_message(tw_engine *e, double global_time, int *accepted);
+
+/* Messages dropped under TW_FLAG_SKIP_OUTDATED since tw_create / tw_reset (logOutdatedMessage, Internal/Event.hs:372). */
+int tw_skipped_outdated(tw_engine *e, uint64_t *count);
 
 /* Partition geometry: first global LP id and LP count owned by this rank. */
 int tw_partition(const tw_engine *e, uint32_t *lp_base, uint32_t *n_local);

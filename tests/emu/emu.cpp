@@ -29,6 +29,10 @@ struct Part {
     std::vector<typename M::State> saved, state;
     std::vector<LPHdr> hdr;
     std::vector<LPIn> in;
+    std::vector<typename M::Event> stage;      // incoming staging rings [sender][parity][stage_cap]
+    std::vector<uint32_t> stage_cnt;           // this partition's sender-side counters
+    std::vector<uint32_t> recv_cnt;            // what the "mailbox" told this partition: messages staged by every sender
+    std::vector<unsigned long long> grp_gvt;
 };
 
 static uint64_t rng_next(uint64_t &s) { s += kGolden; return mix_fin(s); }
@@ -43,6 +47,8 @@ struct WarpPool {
     std::vector<char> smem;
     Acc accs[32];
     const Dev<M> *d = nullptr; uint32_t tile0 = 0; double gvt = 0, wend = 0; uint32_t step = 0; bool quit = false;
+    // group mode (k_run_groups): the warp runs the super-steps of groups [g0, g0 + gpw) back to back
+    bool group_mode = false; uint32_t g0 = 0, gpw = 1, max_rounds = 0; double cap = 0; double graw[32]; uint32_t rounds[32]; bool mine[32];
     WarpPool() : smem(WorkQ<M>::kWarpBytes + 16)
     {
         for (unsigned lane = 0; lane < 32; ++lane) lanes.emplace_back([this, lane] {
@@ -52,8 +58,13 @@ struct WarpPool {
                 if (quit) return;
                 Acc a; a.init();
                 WorkQ<M> q; q.init((void *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15));
-                for (uint32_t t = 0; t < d->tiles; ++t) lp_step<M>(*d, a, q, (tile0 + t) * 32u + lane, gvt, wend, step);
-                q.drain(*d, a, step & 1u);
+                if (group_mode) {
+                    if constexpr (M::kGroup > 1)
+                        mine[lane] = group_rounds<M>(*d, a, q, g0, gpw, max_rounds, step, cap, graw[lane], rounds[lane]);
+                } else {
+                    for (uint32_t t = 0; t < d->tiles; ++t) lp_step<M>(*d, a, q, (tile0 + t) * 32u + lane, gvt, wend, step);
+                    q.drain(*d, a, step & 1u);
+                }
                 accs[lane] = a;
                 done.wait();
             }
@@ -64,6 +75,18 @@ struct WarpPool {
         d = &dev; tile0 = first_tile; gvt = g; wend = w; step = s;
         start.wait(); done.wait();
         for (int i = 0; i < 32; ++i) acc.merge(accs[i]);
+    }
+    // one warp-visit of k_run_groups: returns the rounds run; the groups' GVTs are written back like the kernel does
+    uint32_t run_groups(Dev<M> &dev, uint32_t first_group, uint32_t groups_per_warp, uint32_t budget, uint32_t step0, double bound, Acc &acc)
+    {
+        d = &dev; group_mode = true; g0 = first_group; gpw = groups_per_warp; max_rounds = budget; step = step0; cap = bound;
+        start.wait(); done.wait();
+        group_mode = false;
+        for (int i = 0; i < 32; ++i) {
+            Acc a = accs[i]; a.pend_min = pos_inf(); a.emit_min = pos_inf(); acc.merge(a);
+            if (mine[i] && i % (int)M::kGroup == 0) dev.grp_gvt[first_group + i / M::kGroup] = ordered_bits(graw[i]);
+        }
+        return rounds[0];
     }
     ~WarpPool() { quit = true; start.wait(); for (auto &t : lanes) t.join(); }
 };
@@ -95,13 +118,21 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         P.pages.resize(nl * cap); P.saved.resize(nl * cap); P.state.resize(nl); P.hdr.resize(nl); P.in.resize(nl);
         d.pages = P.pages.data(); d.saved = P.saved.data(); d.state = P.state.data(); d.hdr = P.hdr.data(); d.in = P.in.data();
         for (uint32_t l = 0; l < d.n_local; ++l) {
-            LPHdr h; h.head = h.nproc = h.consumed = h.head_prev = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
+            LPHdr h; h.head = h.np_hp = h.consumed = h.rollbacks = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
             P.hdr[l] = h; LPIn in; in.word = 0; P.in[l] = in;
             P.state[l] = M::initial_state(d.mp, d.lp_base + l);
         }
     }
+    // cross-partition exchange as on the GPUs: staging rings in the receiver's memory, sender-local counters
+    const uint32_t stage_cap = p->outbox_capacity ? p->outbox_capacity : std::max<uint32_t>(8192u, 2u * n_per);
+    for (uint32_t r = 0; r < W; ++r) {
+        parts[r].stage.resize((size_t)W * 2u * stage_cap); parts[r].stage_cnt.assign(kMaxWorld * kCntStride, 0u);
+        parts[r].recv_cnt.assign(kMaxWorld, 0u);
+        parts[r].d.stage_in = parts[r].stage.data(); parts[r].d.stage_cnt = parts[r].stage_cnt.data(); parts[r].d.stage_cap = stage_cap;
+        parts[r].d.flags = p->flags;
+    }
     for (uint32_t r = 0; r < W; ++r)
-        for (uint32_t q = 0; q < W; ++q) { parts[r].d.peer_pages[q] = parts[q].d.pages; parts[r].d.peer_in[q] = parts[q].d.in; }
+        for (uint32_t q = 0; q < W; ++q) parts[r].d.stage_out[q] = parts[q].stage.data() + (size_t)r * 2u * stage_cap;
 
     // initial events through the same routing function the k_route kernel uses
     std::vector<tw_event> init((size_t)p->n_lps * (p->model == TW_MODEL_PHOLD ? p->phold.population : 1) + 8);
@@ -131,16 +162,26 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
         if (p->time_horizon >= 0.0) wend = std::min(wend, gvt + p->time_horizon);
         if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
         acc.init();
+        // k_deliver: every partition routes what the others staged for it during the previous super-step
+        for (uint32_t r = 0; r < W; ++r)
+            for (uint32_t q = 0; q < W; ++q)
+                for (uint32_t j = 0; j < parts[r].recv_cnt[q]; ++j) deliver_staged<M>(parts[r].d, acc, (step & 1u) ^ 1u, q, j);
 #ifdef TW_SIMT_EMU
         for (auto &o : order) pool.run(parts[o.first].d, o.second, gvt, wend, step, acc);
 #else
         for (auto &o : order) { WorkQ<M> q; q.init(nullptr); lp_step<M>(parts[o.first].d, acc, q, o.second, gvt, wend, step); }
 #endif
+        // gvt_exchange_warp: the counts travel with the mailbox entries, the sender's counters start again at zero
+        for (uint32_t r = 0; r < W; ++r)
+            for (uint32_t q = 0; q < W; ++q) {
+                parts[q].recv_cnt[r] = std::min(parts[r].stage_cnt[q * kCntStride], stage_cap);
+                parts[r].stage_cnt[q * kCntStride] = 0u;
+            }
         if (acc.err == TW_ERR_ANTI_UNMATCHED || acc.err == TW_ERR_TIME_ORDER || acc.err == TW_ERR_OUTDATED_MESSAGE) {
             // engine.cu k_diagnose_overflow: an overflowed ring elsewhere is the cause of such an inconsistency
             for (uint32_t r = 0; r < W; ++r)
                 for (uint32_t l = 0; l < parts[r].d.n_local; ++l)
-                    if (in_total(parts[r].in[l].word) - parts[r].hdr[l].head_prev > cap) { acc.err = TW_ERR_QUEUE_OVERFLOW; acc.err_lp = parts[r].d.lp_base + l; }
+                    if (in_total(parts[r].in[l].word) - hdr_head_prev(parts[r].hdr[l]) > cap) { acc.err = TW_ERR_QUEUE_OVERFLOW; acc.err_lp = parts[r].d.lp_base + l; }
         }
         if (acc.err) { fprintf(stderr, "emu: error %u at LP %u step %u\n", acc.err, acc.err_lp, step); return (int)acc.err; }
         if (getenv("EMU_TRACE")) fprintf(stderr, "step %u gvt %.17g exec %u rb %u rollbacks %u strag %u anti %u annih %u retry %u sent %u pend %.17g emit %.17g\n", step, gvt, acc.exec, acc.rb_events, acc.rollbacks, acc.strag, acc.anti, acc.annih, acc.retry, acc.sent_local + acc.sent_remote, acc.pend_min, acc.emit_min);
@@ -158,7 +199,7 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     // as Engine::run: an overflow of the last super-steps has no next drain that would notice it
     for (uint32_t r = 0; r < W; ++r)
         for (uint32_t l = 0; l < parts[r].d.n_local; ++l)
-            if (in_total(parts[r].in[l].word) - parts[r].hdr[l].head_prev > cap) {
+            if (in_total(parts[r].in[l].word) - hdr_head_prev(parts[r].hdr[l]) > cap) {
                 fprintf(stderr, "emu: error %u at LP %u after the last step\n", (unsigned)TW_ERR_QUEUE_OVERFLOW, parts[r].d.lp_base + l);
                 return TW_ERR_QUEUE_OVERFLOW;
             }
@@ -186,6 +227,86 @@ static int emu_run_t(const tw_params *p, uint64_t shuffle_seed, uint64_t *n_exec
     }
     return TW_OK;
 }
+
+#ifdef TW_SIMT_EMU
+// Closed-group models through the warp-local super-step loop (k_run_groups): launches of `budget` rounds until every group
+// has passed the stop time.  gvt_every > 1 plays an external Time Server whose bound lags behind.
+template <class M>
+static int emu_run_groups_t(const tw_params *p, uint64_t shuffle_seed, uint32_t gpw, uint32_t budget, uint64_t *n_exec, uint64_t *hash,
+                            tw_machrep_result *mr, tw_run_stats *st, uint32_t gvt_every)
+{
+    if (p->world > 1 || M::kGroup < 2) return TW_ERR_NOT_SUPPORTED;
+    const uint32_t cap = p->queue_capacity ? p->queue_capacity : 128;
+    Part<M> P; Dev<M> &d = P.d;
+    memset(&d, 0, sizeof d);
+    d.n_global = p->n_lps; d.world = 1; d.rank = 0; d.n_per = p->n_lps; d.lp_base = 0; d.n_local = p->n_lps;
+    d.cap = cap; d.mask = cap - 1; d.tiles = 1; d.closed = 1; d.flags = p->flags;
+    d.max_batch = p->max_events_per_step ? std::min<uint32_t>(p->max_events_per_step, kMaxBatch) : 8;
+    d.proc_limit = p->proc_limit ? p->proc_limit : cap / 4;
+    d.fossil_thresh = p->fossil_threshold ? p->fossil_threshold : cap / 8;
+    if (d.fossil_thresh > d.proc_limit / 2) d.fossil_thresh = d.proc_limit / 2 ? d.proc_limit / 2 : 1;
+    d.stop = p->stop_time; d.horizon = (p->time_horizon >= 0.0) ? p->time_horizon : -1.0;
+    d.mp = M::make_params(*p);
+    const size_t nl = std::max<size_t>(d.n_local, 1);
+    P.pages.resize(nl * cap); P.saved.resize(nl * cap); P.state.resize(nl); P.hdr.resize(nl); P.in.resize(nl);
+    P.stage_cnt.assign(kMaxWorld * kCntStride, 0u);
+    const uint32_t n_groups = d.n_local / M::kGroup;
+    P.grp_gvt.assign(std::max<uint32_t>(n_groups, 1u), ordered_bits(p->start_time));
+    d.pages = P.pages.data(); d.saved = P.saved.data(); d.state = P.state.data(); d.hdr = P.hdr.data(); d.in = P.in.data();
+    d.stage_cnt = P.stage_cnt.data(); d.grp_gvt = P.grp_gvt.data();
+    for (uint32_t l = 0; l < d.n_local; ++l) {
+        LPHdr h; h.head = h.np_hp = h.consumed = h.rollbacks = 0; h.lvt = neg_inf(); h.min_pend = pos_inf();
+        P.hdr[l] = h; LPIn in; in.word = 0; P.in[l] = in;
+        P.state[l] = M::initial_state(d.mp, l);
+    }
+    std::vector<tw_event> init((size_t)p->n_lps + 8);
+    const size_t n_init = M::initial_events(*p, init.data(), init.size());
+    const uint32_t step0 = 2;
+    Acc acc; acc.init();
+    for (size_t i = 0; i < n_init; ++i) route_event<M>(d, acc, (step0 & 1u) ^ 1u, init[i]);
+    if (acc.err) return (int)acc.err;
+    WarpPool<M> pool;
+    std::vector<uint32_t> order;
+    for (uint32_t g = 0; g < n_groups; g += gpw) order.push_back(g);
+    uint64_t rs = shuffle_seed;
+    tw_run_stats S; memset(&S, 0, sizeof S);
+    double bound = gvt_every > 1 ? p->start_time : pos_inf();
+    for (uint64_t launch = 0;; ++launch) {
+        if (launch > 2000000) return TW_ERR_DEADLOCK;
+        if (shuffle_seed) for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng_next(rs) % i]);
+        acc.init();
+        uint32_t max_rounds = 0;
+        for (uint32_t g : order) max_rounds = std::max(max_rounds, pool.run_groups(d, g, gpw, budget, step0, bound, acc));
+        if (acc.err) { fprintf(stderr, "emu groups: error %u at LP %u\n", acc.err, acc.err_lp); return (int)acc.err; }
+        S.steps += max_rounds; S.executed += acc.exec; S.rolled_back += acc.rb_events; S.rollbacks += acc.rollbacks; S.stragglers += acc.strag;
+        S.anti_sent += acc.anti; S.annihilated += acc.annih; S.retries += acc.retry; S.sent_local += acc.sent_local;
+        double local = pos_inf();
+        for (uint32_t g = 0; g < n_groups; ++g) local = std::min(local, from_ordered(P.grp_gvt[g]));
+        S.gvt = std::min(local, bound);
+        if (!(S.gvt <= p->stop_time)) break;
+        if (gvt_every > 1 && launch % gvt_every == gvt_every - 1) bound = local;      // the next GlobalTimeMessage
+    }
+    for (uint32_t l = 0; l < d.n_local; ++l)
+        if (in_total(P.in[l].word) - hdr_head_prev(P.hdr[l]) > cap) return TW_ERR_QUEUE_OVERFLOW;
+    for (uint32_t l = 0; l < d.n_local; ++l) {
+        if (n_exec) n_exec[l] = P.state[l].n_exec;
+        if (hash) hash[l] = P.state[l].hash;
+        S.committed += P.state[l].n_exec; S.trace_hash_sum += P.state[l].hash;
+    }
+    if (st) *st = S;
+    if (mr) { if constexpr (M::kGroup == 3) for (uint32_t lp = 0; lp < p->n_lps; lp += 3) mr[lp / 3] = M::result(P.state[lp], p->stop_time); }
+    return TW_OK;
+}
+extern "C" int emu_run_groups(const tw_params *p, uint64_t shuffle_seed, uint32_t gpw, uint32_t budget, uint32_t gvt_every,
+                              uint64_t *n_exec, uint64_t *hash, tw_machrep_result *mr, tw_run_stats *st)
+{
+    if (gpw < 1) gpw = 1;
+    if (budget < 2) budget = 2;
+    if (p->model == TW_MODEL_MACHREP2) return emu_run_groups_t<MachRepModel>(p, shuffle_seed, gpw, budget & ~1u, n_exec, hash, mr, st, gvt_every);
+    if (p->model == TW_MODEL_MACHREP1) return emu_run_groups_t<MachRep1Model>(p, shuffle_seed, gpw, budget & ~1u, n_exec, hash, mr, st, gvt_every);
+    return TW_ERR_NOT_SUPPORTED;
+}
+#endif
 
 // building blocks of tw_dsl.cuh against the semantics of aivika-transformers' FCFS resource:
 // returns 0 when every scripted step behaves as documented, otherwise the number of the failing check.

@@ -1,5 +1,5 @@
 // simt.hpp -- TEST INFRASTRUCTURE ONLY.  A warp on the CPU: 32 host threads play the lanes, the warp intrinsics the
-// device code uses (__ballot_sync, __any_sync, __shfl_sync, __shfl_xor_sync, __syncwarp) are rendezvous points between
+// device code uses (__ballot_sync, __any_sync, __match_any_sync, __shfl_sync, __shfl_xor_sync, __syncwarp) are rendezvous points between
 // them.  With -DTW_SIMT_EMU tw_core.cuh compiles its *device* code paths (work queue with deferred delivery, whole-warp
 // region search, reconvergence points, warp-uniform loops) for the host, so tests/emu can run exactly what a GPU warp
 // executes against the oracle.  What it cannot show: races between warps and the memory model (warps run one at a time).
@@ -74,6 +74,17 @@ inline T __shfl_sync(unsigned, T v, int src)
 }
 template <class T>
 inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)(simt::g_lane ^ (unsigned)lane_mask)); }
+
+inline unsigned __match_any_sync(unsigned, unsigned v)
+{
+    simt::Warp &w = *simt::g_warp;
+    w.slot[simt::g_lane] = v;
+    w.lanes.wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if ((unsigned)w.slot[i] == v) r |= 1u << i;
+    w.lanes.wait();
+    return r;
+}
 
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }

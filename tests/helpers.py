@@ -206,6 +206,9 @@ def emu_simt():
         L.emu_run_tiles.argtypes = [C.POINTER(ffi.tw_params), C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(ffi.tw_run_stats)]
         L.emu_run_tiles.restype = C.c_int
+        L.emu_run_groups.argtypes = [C.POINTER(ffi.tw_params), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.POINTER(ffi.tw_run_stats)]
+        L.emu_run_groups.restype = C.c_int
         assert L.emu_is_simt() == 1
         _emu_simt = L
     return _emu_simt
@@ -217,6 +220,16 @@ def emu_simt_run(p, shuffle_seed=1, gvt_every=1, tiles=1):
     mr = (ffi.tw_machrep_result * max(1, p.n_lps // 3))()
     st = ffi.tw_run_stats()
     rc = emu_simt().emu_run_tiles(C.byref(p), shuffle_seed, gvt_every, tiles, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
+    return rc, n_exec, h, mr, st
+
+
+def emu_groups_run(p, shuffle_seed=1, gpw=2, budget=64, gvt_every=1):
+    """Closed-group models through the warp-local super-step loop (k_run_groups) on the warp-level emulation."""
+    import numpy as np
+    n_exec = np.zeros(p.n_lps, dtype=np.uint64); h = np.zeros(p.n_lps, dtype=np.uint64)
+    mr = (ffi.tw_machrep_result * max(1, p.n_lps // 3))()
+    st = ffi.tw_run_stats()
+    rc = emu_simt().emu_run_groups(C.byref(p), shuffle_seed, gpw, budget, gvt_every, n_exec.ctypes.data, h.ctypes.data, mr, C.byref(st))
     return rc, n_exec, h, mr, st
 
 

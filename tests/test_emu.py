@@ -225,3 +225,51 @@ def test_warp_level_paths_machrep(H, horizon, batch):
     r1 = H.oracle_machrep1(p1)
     rc, n_exec, h, mr, _ = H.emu_simt_run(p1, 1, 1, 2)
     assert rc == 0 and all(r1[r].up_time_prop == mr[r].up_time_prop for r in range(3))
+
+
+# ---------------------------------------------------------------- closed groups: the warp-local super-step loop (k_run_groups)
+@pytest.mark.parametrize("horizon,batch,gpw,budget,every", [(-1.0, 4, 2, 64, 1), (2.0, 4, 10, 8, 1), (0.0, 1, 1, 2, 1), (-1.0, 16, 3, 1000, 3),
+                                                            (5.0, 8, 4, 2, 7)])
+def test_closed_group_loop_machrep2(H, horizon, batch, gpw, budget, every):
+    """MachRep2 replicas never talk to each other: a warp runs the super-steps of its groups back to back, every group
+    under its own GVT (group_rounds in tw_core.cuh, the body of k_run_groups), for any number of groups per warp, any
+    round budget per launch and a lagging external Time Server bound.  Statistics and traces must equal the oracle's."""
+    p = H.machrep_params(7, 120.0, horizon=horizon, batch=batch, cap=1024)
+    res = H.oracle_machrep(p)
+    rc, n_exec, h, mr, stats = H.emu_groups_run(p, 3, gpw, budget, every)
+    assert rc == 0
+    for r in range(7):
+        assert (res[r].total_up_time, res[r].n_rep, res[r].n_immed_rep) == (mr[r].total_up_time, mr[r].n_rep, mr[r].n_immed_rep)
+        assert res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop
+        assert [res[r].n_exec[k] for k in range(3)] == [int(n_exec[3 * r + k]) for k in range(3)]
+        assert [res[r].hash[k] for k in range(3)] == [int(h[3 * r + k]) for k in range(3)]
+    assert stats.steps % 2 == 0 and stats.executed - stats.rolled_back == stats.committed + 14     # + the 14 START events
+    if horizon != 0.0:
+        assert stats.rolled_back > 0
+
+
+def test_closed_group_loop_machrep1_and_reference_configuration(H):
+    p = H.machrep1_params(4, 300.0, horizon=5.0, batch=8, cap=1024)
+    res = H.oracle_machrep1(p)
+    rc, n_exec, h, mr, stats = H.emu_groups_run(p, 3, 2, 64, 1)
+    assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop and res[r].n_rep == mr[r].n_rep for r in range(4))
+    assert all(res[r].hash[k] == int(h[3 * r + k]) for r in range(4) for k in range(3)) and stats.rolled_back > 0
+    p = H.machrep_params(1, 1000.0)                      # C1: tests/MachRep2DistributedReproducible.hs, no time horizon
+    o = H.oracle_machrep(p)[0]
+    rc, n_exec, h, mr, stats = H.emu_groups_run(p, 1, 1, 4096, 1)
+    assert rc == 0 and o.up_time_prop == mr[0].up_time_prop and o.immed_prop == mr[0].immed_prop
+    assert [o.hash[k] for k in range(3)] == [int(x) for x in h]
+
+
+def test_simulation_retry_really_happens(H):
+    """a19 (handleEventRetry / SimulationRetry, Internal/Event.hs:247-249, 768-813): with unbounded optimism and a large
+    batch the master sees ReleaseRepairPerson before the matching request (resource released above its capacity); the
+    event must stay pending until the straggler's rollback arrives -- and the results must still equal the oracle's."""
+    p = H.machrep_params(64, 200.0, horizon=-1.0, batch=16, cap=1024)
+    res = H.oracle_machrep(p)
+    rc, n_exec, h, mr, stats = H.emu_run(p, 1)
+    assert rc == 0 and stats.retries > 0
+    assert all(res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop for r in range(64))
+    rc, n_exec, h, mr, stats = H.emu_groups_run(H.machrep_params(8, 200.0, horizon=-1.0, batch=16, cap=1024), 2, 3, 256, 1)
+    assert rc == 0 and stats.retries > 0
+    assert all(res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop for r in range(8))

@@ -89,11 +89,14 @@ def test_phold_edge_shapes(H):
     check_phold(H, H.phold_params(64, 6.0, remote_pct=50, population=4, horizon=-1.0, cap=64, proc_limit=4, fossil=2))
 
 
-def test_machrep2_reference_configuration(H):
-    """C1: tests/MachRep2DistributedReproducible.hs, 3 LPs, default DIOParams (no time horizon)."""
+@pytest.mark.parametrize("grouped", [True, False])
+def test_machrep2_reference_configuration(H, grouped):
+    """C1: tests/MachRep2DistributedReproducible.hs, 3 LPs, default DIOParams (no time horizon), through the closed-group
+    kernel (k_run_groups) and through grid-wide super-steps (k_step)."""
     import json, os
     d = D()
-    dio, sim = d.runDIO(d.MachRep2(1), d.DIOParams(queueCapacity=64, stepsPerLaunch=32), d.timeServer(3), d.Specs(0.0, 1000.0))
+    dio, sim = d.runDIO(d.MachRep2(1), d.DIOParams(queueCapacity=64, stepsPerLaunch=32, closedGroupKernel=grouped), d.timeServer(3),
+                        d.Specs(0.0, 1000.0))
     st, n_exec, h, res = sim()
     dio.close()
     o = H.oracle_machrep(H.machrep_params(1, 1000.0))[0]
@@ -105,11 +108,12 @@ def test_machrep2_reference_configuration(H):
     assert st.rolled_back > 0          # unbounded optimism really exercised the rollback path
 
 
+@pytest.mark.parametrize("grouped", [True, False])
 @pytest.mark.parametrize("horizon", [None, 2.0, 0.0])
-def test_machrep2_replicas(H, horizon):
+def test_machrep2_replicas(H, horizon, grouped):
     d = D()
     n = 256
-    dio, sim = d.runDIO(d.MachRep2(n), d.DIOParams(dioTimeHorizon=horizon, queueCapacity=64, stepsPerLaunch=32),
+    dio, sim = d.runDIO(d.MachRep2(n), d.DIOParams(dioTimeHorizon=horizon, queueCapacity=64, stepsPerLaunch=32, closedGroupKernel=grouped),
                         d.timeServer(3 * n), d.Specs(0.0, 300.0))
     st, n_exec, h, res = sim()
     dio.close()
@@ -121,6 +125,24 @@ def test_machrep2_replicas(H, horizon):
         assert rel <= 1e-9 and res[r]["up_time_prop"] == o.up_time_prop          # north_star tolerance, and in fact equal
         assert [int(n_exec[3 * r + k]) for k in range(3)] == [o.n_exec[k] for k in range(3)]
         assert [int(h[3 * r + k]) for k in range(3)] == [o.hash[k] for k in range(3)]
+
+
+def test_simulation_retry_really_happens(H):
+    """a19 (handleEventRetry / SimulationRetry, Internal/Event.hs:247-249, 768-813): unbounded optimism with a large batch
+    makes the master see ReleaseRepairPerson before the request it belongs to; the handler returns H_RETRY, the event stays
+    pending until the straggler's rollback arrives, and the statistics still equal the oracle's.  Both kernels."""
+    d = D()
+    n = 512
+    ores = H.oracle_machrep(H.machrep_params(n, 200.0))
+    for grouped in (True, False):
+        dio, sim = d.runDIO(d.MachRep2(n), d.DIOParams(queueCapacity=1024, maxEventsPerStep=16, stepsPerLaunch=32, closedGroupKernel=grouped),
+                            d.timeServer(3 * n), d.Specs(0.0, 200.0))
+        st, n_exec, h, res = sim()
+        dio.close()
+        assert st.retries > 0 and st.rolled_back > 0
+        assert (res["up_time_prop"] == np.array([r.up_time_prop for r in ores])).all()
+        assert (res["immed_prop"] == np.array([r.immed_prop for r in ores])).all()
+        assert (h == np.array([r.hash[k] for r in ores for k in range(3)], dtype=np.uint64)).all()
 
 
 @pytest.mark.parametrize("horizon", [None, 5.0, 0.0])
@@ -217,12 +239,45 @@ def test_full_size_c3_invariants(H):
 def test_full_size_c4_c5_invariants(H):
     """1M-LP / 50 % remote (configs[3]) and the skewed 256K-LP case (configs[4]) on one GPU, short stop time:
     the committed trace is identical for a conservative and an optimistic window, and run-to-run."""
-    for kw, cap in ((dict(n_lps=1 << 20, remote_pct=50), 128), (dict(n_lps=1 << 18, remote_pct=50, n_hot=4096, hot_pct=10), 512)):
+    for kw, cap, batch in ((dict(n_lps=1 << 20, remote_pct=50), 128, 4), (dict(n_lps=1 << 18, remote_pct=50, n_hot=1024, hot_pct=50), 4096, 64)):
         sigs = []
         for horizon in (0.1, 0.5, 0.5):
-            st, n_exec, h = run_phold(H, H.phold_params(stop=2.0, horizon=horizon, cap=cap, **kw))
+            st, n_exec, h = run_phold(H, H.phold_params(stop=2.0, horizon=horizon, cap=cap, batch=batch, **kw))
             sigs.append((int(st.committed), int(st.trace_hash_sum)))
         assert sigs[0] == sigs[1] == sigs[2]
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5"])
+def test_benched_configurations_equal_the_oracle_at_full_size(H, name):
+    """Every BASELINE configuration exactly as bench.py runs it (full LP count, full stop time, the benched window, batch
+    and ring) against the oracle's answer for that configuration (tests/golden/full_configs.json, generated by
+    tests/golden/make_golden_full.py from oracle/oracle.c): committed count, trace-hash sum, the LP-bound digest of the
+    per-LP (count, hash) pairs and, for MachRep2, the digest of the per-replica results and the documented means."""
+    import json, os
+    from aivika_distributed_b200 import workloads as W
+    d = D()
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "full_configs.json")))[name]
+    wl = W.WORKLOADS[name]
+    ps = d.DIOParams(dioTimeHorizon=None if wl["horizon"] < 0 else wl["horizon"], queueCapacity=wl["cap"], maxEventsPerStep=wl["batch"])
+    if wl["kind"] == "phold":
+        model = d.PHOLD(wl["n_lps"], 16, wl["remote_pct"], 0.1, 1.0, W.SEED, wl.get("n_hot", 0), wl.get("hot_pct", 0))
+    else:
+        model = d.MachRep2(wl["n_replicas"])
+    dio, sim = d.runDIO(model, ps, d.timeServer(1), d.Specs(0.0, wl["stop"]))
+    try:
+        out = sim()
+    finally:
+        dio.close()
+    st, n_exec, h = out[0], out[1], out[2]
+    assert int(st.committed) == fx["committed"] and hex(int(st.trace_hash_sum)) == fx["trace_hash_sum"]
+    assert hex(W.lp_digest(0, n_exec, h)) == fx["lp_digest"]
+    if wl["kind"] == "machrep":
+        res = out[3]
+        assert hex(W.machrep_digest(0, res)) == fx["replica_digest"]
+        assert abs(res["up_time_prop"].mean() - fx["mean_up_time_prop"]) < 1e-12 and abs(res["up_time_prop"].mean() - 0.6) < 0.02
+        assert abs(res["immed_prop"].mean() - fx["mean_immed_prop"]) < 1e-12 and abs(res["immed_prop"].mean() - 0.667) < 0.02
+    if name == "c5":
+        assert st.committed / st.executed < 0.99          # rollback-heavy, as BASELINE configs[4] says
 
 
 def test_errors_are_reported_through_status_codes(H):
@@ -244,11 +299,23 @@ def test_errors_are_reported_through_status_codes(H):
         dio.enqueueMessage(3, 1.0, src=0, send_time=2.0)
     assert e.value.code == 3
     dio.close()
-    dio = d.DIO(d.PHOLD(64), d.DIOParams(), d.Specs(1.0, 5.0))
+    dio = d.DIO(d.PHOLD(64), d.DIOParams(dioAllowSkippingOutdatedMessage=False), d.Specs(1.0, 5.0))
     with pytest.raises(d.SimulationAbort) as e:
         dio.enqueueMessage(3, 0.5, src=0, send_time=0.5)
     assert e.value.code == 4
     dio.close()
+    # the reference's default (dioAllowSkippingOutdatedMessage = True, Internal/DIO.hs:206): logged and skipped
+    dio = d.DIO(d.PHOLD(64), d.DIOParams(), d.Specs(1.0, 5.0))
+    dio.enqueueMessage(3, 0.5, src=0, send_time=0.5)
+    dio.enqueueMessage(3, 1.5, src=0, send_time=1.0)
+    assert dio.skippedOutdatedMessages() == 1
+    st = dio.runEventInStopTime()
+    assert st.committed >= 1
+    dio.close()
+    # a ring larger than the 16-bit fields of the LP header allow is refused
+    with pytest.raises(d.SimulationAbort) as e:
+        d.DIO(d.PHOLD(64), d.DIOParams(queueCapacity=65536), d.Specs(0.0, 5.0))
+    assert e.value.code == 1
 
 
 def test_resume_and_time_server_role(H):
@@ -267,6 +334,9 @@ def test_resume_and_time_server_role(H):
     assert (n_exec == o_exec).all() and (h == o_hash).all()
     s = dio.logicalProcessState(17)
     assert s.lpStateId == 17 and s.lpStateLocalTime <= 6.0 and s.lpStateEventQueueTime > 6.0 and s.lpStateEventQueueSize > 0
+    # lpStateRollbackCount is per LP (Optimistic/State.hs:50): the counts of all LPs add up to the engine's total
+    per_lp = [dio.logicalProcessState(lp).lpStateRollbackCount for lp in range(1000)]
+    assert sum(per_lp) == st1.rollbacks + st2.rollbacks and max(per_lp) > 0 and max(per_lp) < sum(per_lp)
     # reset + rerun gives the same trace
     dio.reset(); dio.enqueueMessages(dio.initialEvents()); dio.runEventInStopTime()
     n2, h2 = dio.lpStats()
