@@ -22,7 +22,7 @@ ERROR_NAMES = {
     0: "TW_OK", 1: "TW_ERR_INVALID_ARG", 2: "TW_ERR_CUDA", 3: "TW_ERR_SEND_AFTER_RECV",
     4: "TW_ERR_OUTDATED_MESSAGE", 5: "TW_ERR_QUEUE_OVERFLOW", 6: "TW_ERR_ANTI_UNMATCHED",
     7: "TW_ERR_DEADLOCK", 8: "TW_ERR_TIME_ORDER", 9: "TW_ERR_BAD_DESTINATION", 10: "TW_ERR_MODEL",
-    11: "TW_ERR_OUTBOX_OVERFLOW", 12: "TW_ERR_NOT_SUPPORTED",
+    11: "TW_ERR_OUTBOX_OVERFLOW", 12: "TW_ERR_NOT_SUPPORTED", 13: "TW_ERR_ABORTED",
 }
 
 # every symbol include/twb200.h declares (checked by tests/test_abi.py)
@@ -30,6 +30,8 @@ EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
     "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range",
     "tw_attach_time_server", "tw_local_time", "tw_global_time_message", "tw_skipped_outdated",
+    "tw_wire_create", "tw_wire_destroy", "tw_wire_encode_message", "tw_wire_decode_message", "tw_wire_encode_lp_message",
+    "tw_wire_decode_lp_message", "tw_wire_encode_ts_message", "tw_wire_decode_ts_message", "tw_wire_handle_lp_message",
     "tw_nccl_unique_id", "tw_last_error", "tw_strerror", "tw_version", "tw_kernel_launch_count",
 ]
 
@@ -88,6 +90,14 @@ class tw_monitor_state(C.Structure):
                 ("sent_local", C.c_uint64), ("sent_remote", C.c_uint64), ("n_lps_local", C.c_uint32), ("rank", C.c_uint32)]
 
 
+class tw_wire_pid(C.Structure):
+    _fields_ = [("node_address", C.c_char_p), ("address_len", C.c_uint32), ("lpid_unique", C.c_int32), ("lpid_counter", C.c_int32)]
+
+
+class tw_wire_type(C.Structure):
+    _fields_ = [("fingerprint", C.c_uint8 * 16), ("payload", C.c_uint32)]
+
+
 MONITOR_FN = C.CFUNCTYPE(None, C.POINTER(tw_monitor_state), C.c_void_p)
 
 _lib = None
@@ -125,6 +135,19 @@ def load(path=None):
     lib.tw_model_initial_events_range.argtypes = [C.POINTER(tw_params), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
                                                   C.POINTER(C.c_size_t)]
     lib.tw_model_initial_events_range.restype = C.c_int
+    U8P, SZP = C.c_void_p, C.POINTER(C.c_size_t)
+    lib.tw_wire_create.argtypes = [C.POINTER(tw_wire_pid), C.c_uint32, C.POINTER(tw_wire_type), C.c_uint32, C.POINTER(H)]
+    lib.tw_wire_destroy.argtypes = [H]
+    lib.tw_wire_encode_message.argtypes = [H, C.POINTER(tw_event), U8P, C.c_size_t, SZP]
+    lib.tw_wire_decode_message.argtypes = [H, U8P, C.c_size_t, C.POINTER(tw_event), SZP]
+    lib.tw_wire_encode_lp_message.argtypes = [H, C.c_uint32, C.c_void_p, C.c_size_t, C.c_double, U8P, C.c_size_t, SZP]
+    lib.tw_wire_decode_lp_message.argtypes = [H, U8P, C.c_size_t, C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t, SZP, C.POINTER(C.c_double)]
+    lib.tw_wire_encode_ts_message.argtypes = [H, C.c_uint32, C.c_uint32, C.c_double, U8P, C.c_size_t, SZP]
+    lib.tw_wire_decode_ts_message.argtypes = [H, U8P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    lib.tw_wire_handle_lp_message.argtypes = [H, H, C.c_uint32, U8P, C.c_size_t, U8P, C.c_size_t, SZP, C.POINTER(C.c_uint32)]
+    for f in ("tw_wire_create", "tw_wire_destroy", "tw_wire_encode_message", "tw_wire_decode_message", "tw_wire_encode_lp_message",
+              "tw_wire_decode_lp_message", "tw_wire_encode_ts_message", "tw_wire_decode_ts_message", "tw_wire_handle_lp_message"):
+        getattr(lib, f).restype = C.c_int
     lib.tw_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8 * 128)]; lib.tw_nccl_unique_id.restype = C.c_int
     lib.tw_last_error.argtypes = [H]; lib.tw_last_error.restype = C.c_char_p
     lib.tw_strerror.argtypes = [C.c_int]; lib.tw_strerror.restype = C.c_char_p

@@ -533,6 +533,7 @@ static const char *code_name(int c)
     case TW_ERR_MODEL: return "a model declared as closed groups sent a message outside the sender's group";
     case TW_ERR_OUTBOX_OVERFLOW: return "cross-GPU staging ring full (raise tw_params.outbox_capacity)";
     case TW_ERR_NOT_SUPPORTED: return "not supported";
+    case TW_ERR_ABORTED: return "Aborted the simulation (AbortSimulationMessage)";
     default: return "unknown error";
     }
 }

@@ -40,7 +40,8 @@ enum {
     TW_ERR_BAD_DESTINATION    = 9,   /* receiver id outside [0, n_lps) */
     TW_ERR_MODEL              = 10,  /* a model registered as closed groups sent a message outside the sender's group */
     TW_ERR_OUTBOX_OVERFLOW    = 11,  /* cross-GPU staging ring full: raise tw_params.outbox_capacity */
-    TW_ERR_NOT_SUPPORTED      = 12
+    TW_ERR_NOT_SUPPORTED      = 12,
+    TW_ERR_ABORTED            = 13   /* AbortSimulationMessage received: SimulationAbort, Internal/Event.hs:476-484 */
 };
 
 enum { TW_MODEL_PHOLD = 1, TW_MODEL_MACHREP2 = 2, TW_MODEL_MACHREP1 = 3 };
@@ -245,6 +246,64 @@ int tw_model_initial_events(const tw_params *params, tw_event *out, size_t cap, 
 /* Same, restricted to the start-time messages addressed to LPs lp_begin <= lp < lp_end (a rank's slice). */
 int tw_model_initial_events_range(const tw_params *params, uint32_t lp_begin, uint32_t lp_end,
                                   tw_event *out, size_t cap, size_t *n);
+
+/*
+ * The reference's wire format at the boundary (csrc/tw_wire.cpp).  `Message`,
+ * `LogicalProcessMessage` and `TimeServerMessage` (Internal/Message.hs:37-54, 113-137, 140-156) are encoded exactly as their
+ * GHC.Generics `Binary` instances lay them out, so that a device partition can exchange bytes with Cloud Haskell processes:
+ * receive QueueMessage / QueueMessageBulk from CPU logical processes (relayed by the inbox process, Internal/DIO.hs:366-370),
+ * and sit under a stock `timeServer` (ComputeLocalTimeMessage in, LocalTimeMessage out, GlobalTimeMessage in).
+ * Byte-level parity is UNPINNED against GHC (no toolchain here): see the header of tw_wire.cpp.
+ */
+typedef struct tw_wire_ctx tw_wire_ctx;
+/* DP.ProcessId of one logical process: NodeId (the EndPointAddress bytes, e.g. "127.0.0.1:8088:0") + LocalProcessId. */
+typedef struct tw_wire_pid {
+    const uint8_t *node_address;
+    uint32_t address_len;
+    int32_t  lpid_unique, lpid_counter;
+} tw_wire_pid;
+/* How the (type, value) pair of a tw_event maps onto the Haskell message data type of that kind. */
+enum {
+    TW_WIRE_PAYLOAD_NONE           = 0,   /* constructor without fields */
+    TW_WIRE_PAYLOAD_SRC_PID        = 1,   /* C DP.ProcessId           (tests/MachRep2DistributedReproducible.hs:89 ...Resp: the sender's id) */
+    TW_WIRE_PAYLOAD_SRC_PID_DOUBLE = 2,   /* C (DP.ProcessId, Double) (:88 TotalUpTimeChange) */
+    TW_WIRE_PAYLOAD_SRC_PID_INT    = 3,   /* C (DP.ProcessId, Int)    (:91 NRepChange, :94 NImmedRepChange, :98 RepairPersonCountResp) */
+    TW_WIRE_PAYLOAD_DOUBLE         = 4,   /* C Double                 (tests/MachRep1.hs:46 TotalUpTimeChange) */
+    TW_WIRE_PAYLOAD_INT            = 5,   /* C Int */
+    TW_WIRE_PAYLOAD_SRC_INT_CTR    = 6    /* C Int Word64: sender LP index and send counter (hs/PHOLD.hs `Job`) */
+};
+typedef struct tw_wire_type {
+    uint8_t  fingerprint[16];             /* encodeFingerprint (fingerprint (undefined :: T)): supplied by the Haskell side */
+    uint32_t payload;                     /* TW_WIRE_PAYLOAD_* */
+} tw_wire_type;
+/* constructor indices of LogicalProcessMessage (Internal/Message.hs:113-137) and TimeServerMessage (:140-156) */
+enum { TW_WIRE_QUEUE_MESSAGE = 0, TW_WIRE_QUEUE_MESSAGE_BULK = 1, TW_WIRE_COMPUTE_LOCAL_TIME = 4, TW_WIRE_GLOBAL_TIME = 5,
+       TW_WIRE_ABORT_SIMULATION = 9 };
+enum { TW_WIRE_TS_REGISTER = 0, TW_WIRE_TS_UNREGISTER = 1, TW_WIRE_TS_TERMINATE = 2, TW_WIRE_TS_COMPUTE_LOCAL_TIME_ACK = 3,
+       TW_WIRE_TS_REQUEST_GLOBAL_TIME = 4, TW_WIRE_TS_LOCAL_TIME = 5, TW_WIRE_TS_PROVIDE_STATE = 6 };
+
+/* pids[lp] for every LP id that can occur as sender or receiver; types[kind] for every tw_event.type in use. */
+int tw_wire_create(const tw_wire_pid *pids, uint32_t n_lps, const tw_wire_type *types, uint32_t n_types, tw_wire_ctx **out);
+int tw_wire_destroy(tw_wire_ctx *ctx);
+/* `encode (m :: Message)`.  Encoders return TW_ERR_INVALID_ARG with *len = bytes needed when cap is too small. */
+int tw_wire_encode_message(const tw_wire_ctx *ctx, const tw_event *ev, uint8_t *buf, size_t cap, size_t *len);
+int tw_wire_decode_message(const tw_wire_ctx *ctx, const uint8_t *buf, size_t len, tw_event *ev, size_t *consumed);
+/* `encode (m :: LogicalProcessMessage)`: kind = TW_WIRE_QUEUE_MESSAGE (n = 1), _BULK (n events), _COMPUTE_LOCAL_TIME, _GLOBAL_TIME
+ * (time), _ABORT_SIMULATION.  The decoder returns TW_ERR_INVALID_ARG with *n = events needed when evs_cap is too small. */
+int tw_wire_encode_lp_message(const tw_wire_ctx *ctx, uint32_t kind, const tw_event *evs, size_t n, double time,
+                              uint8_t *buf, size_t cap, size_t *len);
+int tw_wire_decode_lp_message(const tw_wire_ctx *ctx, const uint8_t *buf, size_t len, uint32_t *kind, tw_event *evs, size_t evs_cap,
+                              size_t *n, double *time);
+/* `encode (m :: TimeServerMessage)`: kind = TW_WIRE_TS_*, lp = the logical process named in it, time for LocalTimeMessage. */
+int tw_wire_encode_ts_message(const tw_wire_ctx *ctx, uint32_t kind, uint32_t lp, double time, uint8_t *buf, size_t cap, size_t *len);
+int tw_wire_decode_ts_message(const tw_wire_ctx *ctx, const uint8_t *buf, size_t len, uint32_t *kind, uint32_t *lp, double *time);
+/* processChannelMessage (Internal/Event.hs:358-449) for a device partition registered under the ProcessId of LP self_lp:
+ * QueueMessage / QueueMessageBulk -> tw_enqueue_messages; GlobalTimeMessage t -> tw_global_time_message;
+ * ComputeLocalTimeMessage -> the replies ComputeLocalTimeAcknowledgementMessage pid and LocalTimeMessage pid t
+ * (Internal/DIO.hs:560-566, 655-664), each preceded by its length as a little-endian uint32; AbortSimulationMessage ->
+ * TW_ERR_ABORTED. */
+int tw_wire_handle_lp_message(tw_engine *e, const tw_wire_ctx *ctx, uint32_t self_lp, const uint8_t *buf, size_t len,
+                              uint8_t *replies, size_t cap, size_t *replies_len, uint32_t *n_replies);
 
 /* ncclGetUniqueId for multi-GPU runs; rank 0 calls it and distributes the 128 bytes. */
 int tw_nccl_unique_id(uint8_t out[128]);
