@@ -616,13 +616,14 @@ struct Engine : EngineBase {
         TW_CUDA(cudaMemset(d.ctl, 0, sizeof(Ctl)));
         TW_CUDA(cudaMalloc(&d.stage_cnt, kMaxWorld * kCntStride * sizeof(uint32_t)));
         TW_CUDA(cudaMemset(d.stage_cnt, 0, kMaxWorld * kCntStride * sizeof(uint32_t)));
-        // Closed groups (replicas): a warp iterates the super-steps of its groups inside one launch (k_run_groups).  As many
-        // warps as the GPU keeps resident, each with as few groups as that allows: a round costs one latency chain however
-        // many lanes are busy.
+        // Closed groups (replicas): a warp iterates the super-steps of its groups inside one launch (k_run_groups).  A round
+        // costs the same instructions however many lanes are busy, so lanes are packed -- but not to the point where an SM
+        // has fewer warps than it needs to hide their latency: about six warps per SM (measured on c2: 2 groups per warp
+        // 0.26, 5 groups 0.42, 10 groups 0.37 G events/s; profiles/r2_tuning.md).
         if constexpr (M::kGroup > 1) if (!(p.flags & kFlagNoGroupKernel) && !getenv("TWB200_NO_GROUP_KERNEL")) {
             group_kernel = true;
             const uint32_t n_groups = d.n_local / M::kGroup;
-            const uint32_t resident = (uint32_t)prop.multiProcessorCount * 16u;
+            const uint32_t resident = (uint32_t)prop.multiProcessorCount * 6u;
             gpw = (n_groups + resident - 1) / resident; if (gpw < 1) gpw = 1;
             const uint32_t max_gpw = 32u / M::kGroup; if (gpw > max_gpw) gpw = max_gpw;
             if (const char *e = getenv("TWB200_GROUPS_PER_WARP")) { const long v = atol(e); if (v >= 1 && v <= (long)max_gpw) gpw = (uint32_t)v; }
@@ -846,6 +847,34 @@ struct Engine : EngineBase {
         return TW_OK;
     }
 
+    // Diagnostic (TWB200_TIME_KERNELS=1): the super-steps launched one by one with CUDA events around every kernel, no graph,
+    // no overlap between consecutive launches.  Prints the average duration of k_deliver and k_step to stderr.
+    int run_timed(double until, Ctl &last, bool &finished)
+    {
+        cudaEvent_t e[3]; for (auto &x : e) TW_CUDA(cudaEventCreate(&x));
+        double t_deliver = 0, t_step = 0; uint64_t n = 0;
+        while (!finished) {
+            TW_CUDA(cudaEventRecord(e[0], stream));
+            if (P.world > 1) { k_deliver<M><<<deliver_grid, kBlock, 0, stream>>>(d); count(1); }
+            TW_CUDA(cudaEventRecord(e[1], stream));
+            k_step<M><<<step_grid, kBlock, stage_bytes(), stream>>>(d); count(1);
+            if (P.world > 1 && !d.fused_gvt) { k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.stage_cnt, d.rank, d.world, d.peer_timeout_ns); count(1); }
+            TW_CUDA(cudaEventRecord(e[2], stream));
+            TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+            TW_CUDA(cudaStreamSynchronize(stream));
+            float a = 0, b = 0; cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]);
+            t_deliver += a; t_step += b; ++n;
+            last = h_ctl[0];
+            int rc = check_device_error(last); if (rc) return rc;
+            if (!(last.gvt <= until)) finished = true;
+            if (n > 1000000) break;
+        }
+        fprintf(stderr, "[twb200 rank %u] %llu super-steps: k_deliver %.2f us, k_step%s %.2f us on average\n", d.rank, (unsigned long long)n,
+                1e3 * t_deliver / (double)(n ? n : 1), d.fused_gvt ? " (+ fused GVT round)" : " + k_gvt_exchange", 1e3 * t_step / (double)(n ? n : 1));
+        for (auto &x : e) cudaEventDestroy(x);
+        return TW_OK;
+    }
+
     int run(double until, tw_run_stats *st) override
     {
         if (!(until <= P.stop_time)) until = P.stop_time;
@@ -866,6 +895,7 @@ struct Engine : EngineBase {
         double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
         Ctl last = c0;
         if (group_kernel) { if constexpr (M::kGroup > 1) result = run_groups(until, c0, last, finished); }
+        else if (getenv("TWB200_TIME_KERNELS")) result = run_timed(until, last, finished);
         else while (!finished) {
             TW_CUDA(cudaGraphLaunch(graph, stream)); count(launches_per_graph(B));
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));

@@ -535,16 +535,6 @@ TW_NOINLINE bool key_less_at(const typename M::Event *pg, uint32_t mask, uint32_
     return key_less(x, y);
 }
 
-// Two candidates fell into one time quantum.  That is harmless only when both are tombstones with the very same receive
-// time (an annihilated message and its anti-message): no-ops whose mutual order does not matter.  (A live entry next
-// to a tombstone is not let through: two live entries could tie through the tombstone between them.)
-template <class M>
-TW_NOINLINE bool tie_is_harmless(const typename M::Event *pg, uint32_t mask, uint32_t beg, uint32_t a, uint32_t b)
-{
-    const typename M::Event x = pg[(beg + a) & mask], y = pg[(beg + b) & mask];
-    return x.recv_ts == y.recv_ts && (x.ctr & (kAntiBit | kDeadBit)) != 0 && (y.ctr & (kAntiBit | kDeadBit)) != 0;
-}
-
 // Minimum by full key over n pending records starting at ring index beg (sequential; the CPU emulation's search
 // for long regions and the tie fallback of the cooperative search).
 template <class M>
@@ -561,29 +551,60 @@ TW_NOINLINE uint32_t min_by_full_key(const typename M::Event *pg, uint32_t mask,
 
 #if TW_SIMT
 // Cooperative search of a long pending region (more than kMaskBits entries): the whole warp looks for the
-// earliest record of the leader's region, 32 records per load.  All lanes call it with the leader's arguments;
-// the result is meaningful on every lane.  `tie` reports that the minimum receive time occurs more than once.
+// earliest record of the leader's region, 32 records per load (four loads in flight per lane).  All lanes call it with
+// the leader's arguments; the result is meaningful on every lane.  When the minimum receive time occurs more than once
+// (typically an annihilated message and its anti-message, both waiting to be skipped as no-ops) the order is settled by
+// the full key (send time, sender, counter) -- also cooperatively: a second pass over the records of that time.
 template <class M>
 __device__ __forceinline__ void coop_min(const typename M::Event *lpg, uint32_t mask, uint32_t beg, uint32_t n,
-                                         double &ts_out, uint32_t &ix_out, bool &tie_out)
+                                         double &ts_out, uint32_t &ix_out)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    double bts = pos_inf(); uint32_t bix = 0; bool tie = false;
-    for (uint32_t k = lane; k < n; k += 32u) {
-        const double ts = lpg[(beg + k) & mask].recv_ts;
-        if (ts < bts) { bts = ts; bix = k; tie = false; }
-        else if (ts == bts) tie = true;
+    const unsigned long long kInf = ordered_bits(pos_inf());    // "nothing": an empty region reports +inf
+    unsigned long long bo = kInf; uint32_t bix = 0; bool tie = false;
+    for (uint32_t k = lane; k < n; k += 128u) {
+        unsigned long long o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t kk = k + 32u * (uint32_t)u;
+            o[u] = kk < n ? ordered_bits(lpg[(beg + kk) & mask].recv_ts) : kInf;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (o[u] < bo) { bo = o[u]; bix = k + 32u * (uint32_t)u; tie = false; }
+            else if (o[u] == bo && o[u] != kInf) tie = true;
+        }
     }
-    unsigned long long v = ordered_bits(bts);
+    unsigned long long v = bo;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
-    const bool mine = (ordered_bits(bts) == v) && n > 0;
+    const bool mine = (bo == v) && v != kInf;
     const unsigned win = __ballot_sync(0xffffffffu, mine);
     const unsigned tw = __ballot_sync(0xffffffffu, mine && tie);
-    const int w = win ? __ffs(win) - 1 : 0;
-    ix_out = __shfl_sync(0xffffffffu, bix, w);
     ts_out = from_ordered(v);
-    tie_out = (tw != 0u) || (__popc(win) > 1);
+    if (tw == 0u && __popc(win) <= 1) {                       // a unique minimum
+        ix_out = __shfl_sync(0xffffffffu, bix, win ? __ffs((int)win) - 1 : 0);
+        return;
+    }
+    // second pass: among the records with that receive time, the smallest (send time, sender, counter)
+    unsigned long long bs = ~0ull, bc = ~0ull; uint32_t bsrc = 0xFFFFFFFFu; bix = 0;
+    for (uint32_t k = lane; k < n; k += 32u) {
+        const typename M::Event *pe = lpg + ((beg + k) & mask);
+        if (ordered_bits(pe->recv_ts) != v) continue;
+        const unsigned long long so = ordered_bits(pe->send_ts), c = pe->ctr & kCtrMask; const uint32_t sr = pe->src;
+        if (so < bs || (so == bs && (sr < bsrc || (sr == bsrc && c < bc)))) { bs = so; bsrc = sr; bc = c; bix = k; }
+    }
+    unsigned long long ms = bs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, ms, o); ms = t < ms ? t : ms; }
+    uint32_t msrc = (bs == ms) ? bsrc : 0xFFFFFFFFu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const uint32_t t = __shfl_xor_sync(0xffffffffu, msrc, o); msrc = t < msrc ? t : msrc; }
+    unsigned long long mc = (bs == ms && bsrc == msrc) ? bc : ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, mc, o); mc = t < mc ? t : mc; }
+    const unsigned w2 = __ballot_sync(0xffffffffu, bs == ms && bsrc == msrc && bc == mc && bs != ~0ull);
+    ix_out = __shfl_sync(0xffffffffu, bix, w2 ? __ffs((int)w2) - 1 : 0);    // identical keys (twins): any of them
 }
 #endif
 
@@ -823,14 +844,31 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
                 }
             }
             if (rest_bits != ~0ull) rest_min = dmin(rest_min, bits2d(rest_bits));
-            // two in-window entries in one quantum: their order needs the exact key
+            // Two or more in-window entries in one time quantum: their order needs the exact key (receive time, send time,
+            // sender, counter).  The list is sorted by quantum, so such entries are neighbours: an exact insertion sort of
+            // the (at most kCand) candidates settles every run of equal quanta -- MachRep2 sends three messages with one
+            // receive time per failure (tests/MachRep2DistributedReproducible.hs:133-135), so for that model this is the
+            // common case, not the exception.  An annihilated message and its anti-message have identical keys: their
+            // mutual order does not matter (both are skipped as no-ops).
             bool tie = false;
+            bool any_run = false;
 #pragma unroll
-            for (int i = 0; i + 1 < kCand; ++i)
-                if (c[i + 1] != kNoCand && (c[i] >> 5) == (c[i + 1] >> 5))
-                    tie = tie || !tie_is_harmless<M>(pg, mask, rbeg, c[i] & 31u, c[i + 1] & 31u);
+            for (int i = 0; i + 1 < kCand; ++i) any_run = any_run || (c[i + 1] != kNoCand && (c[i] >> 5) == (c[i + 1] >> 5));
+            if (any_run) {
+#pragma unroll
+                for (int i = 1; i < kCand; ++i) {
+                    bool moving = true;
+#pragma unroll
+                    for (int j = i; j > 0; --j) {
+                        moving = moving && c[j] != kNoCand && (c[j - 1] >> 5) == (c[j] >> 5) &&
+                                 key_less_at<M>(pg, mask, rbeg, c[j] & 31u, c[j - 1] & 31u);
+                        const uint32_t lo = moving ? c[j] : c[j - 1], hi = moving ? c[j - 1] : c[j];
+                        c[j - 1] = lo; c[j] = hi;
+                    }
+                }
+            }
             // the last candidate shares its quantum with an entry that did not fit into the list: `drop` is only the
-            // first of possibly several such entries, so no harmless-pair shortcut here
+            // first of possibly several such entries -> the exact search over the whole region
             if (drop != kNoCand && (c[kCand - 1] >> 5) == (drop >> 5)) tie = true;
             if (tie) { heavy = true; searched = false; }
             need_scan = false;
@@ -850,12 +888,9 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
                 const Event *lpg = reinterpret_cast<const Event *>(__shfl_sync(0xffffffffu, (unsigned long long)pg, leader));
                 const uint32_t lbeg = __shfl_sync(0xffffffffu, pbeg + done, leader);
                 const uint32_t ln = __shfl_sync(0xffffffffu, nreg - done, leader);
-                double ts_; uint32_t ix_; bool tie_;
-                coop_min<M>(lpg, mask, lbeg, ln, ts_, ix_, tie_);
-                if ((int)(threadIdx.x & 31u) == leader) {
-                    bts = ts_; bix = ix_;
-                    if (tie_) bix = min_by_full_key<M>(pg, mask, pbeg + done, nreg - done, &bts);
-                }
+                double ts_; uint32_t ix_;
+                coop_min<M>(lpg, mask, lbeg, ln, ts_, ix_);
+                if ((int)(threadIdx.x & 31u) == leader) { bts = ts_; bix = ix_; }
             }
 #else
             if (want && heavy && nreg > done) bix = min_by_full_key<M>(pg, mask, pbeg + done, nreg - done, &bts);

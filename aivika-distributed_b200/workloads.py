@@ -24,7 +24,7 @@ WORKLOADS = {
                kind="phold", n_lps=1 << 18, remote_pct=50, n_hot=1024, hot_pct=50, stop=20.0, horizon=0.5, batch=64, cap=4096,
                cpu_stop=1.0),
     "c2": dict(desc="MachRep2DistributedReproducible replicated as 4096 independent 3-LP groups, stop 1000 (BASELINE configs[1])",
-               kind="machrep", n_replicas=4096, stop=1000.0, horizon=2.0, batch=4, cap=256, cpu_stop=1000.0),
+               kind="machrep", n_replicas=4096, stop=1000.0, horizon=1e-4, batch=4, cap=256, cpu_stop=1000.0),
     "c1": dict(desc="tests/MachRep2DistributedReproducible.hs: master + 2 slaves, seeds 456/789, stop 1000 (BASELINE configs[0])",
                kind="machrep", n_replicas=1, stop=1000.0, horizon=-1.0, batch=4, cap=64, cpu_stop=1000.0),
 }
