@@ -167,7 +167,7 @@ __device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, ui
             ctl->pend_min = ordered_bits(pos_inf());
             ctl->emit_min = ordered_bits(pos_inf());
             ctl->step = step + 1; ctl->c_steps += 1;
-            ctl->done_blocks = 0;
+            ctl->done_blocks = 0; ctl->tile_next = 0;
             __threadfence();
         }
         __syncwarp();
@@ -195,10 +195,21 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
         extern __shared__ uint4 tw_queue_smem[];             // per warp: work queue + held messages (tw_core.cuh, WorkQ)
         WorkQ<M> q;
         q.init(reinterpret_cast<char *>(tw_queue_smem) + (threadIdx.x >> 5) * WorkQ<M>::kWarpBytes);
-        // one warp = d.tiles consecutive tiles of 32 LPs; the work queue is carried from tile to tile
-        const uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
-        for (uint32_t t = 0; t < d.tiles; ++t)
-            lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+        // Persistent warps: the grid is sized to the resident warps of the GPU, not to the partition.  A warp starts with
+        // the d.tiles consecutive tiles of 32 LPs its position in the grid gives it and then takes further ones from the
+        // partition's tile counter until none is left -- no warp slot idles at a block's end while the slowest warp of that
+        // block finishes.  The next assignment is requested before the current tiles are run, so its round trip is hidden.
+        // The work queue is carried from tile to tile.
+        const uint32_t n_tiles = (d.n_local + 31u) >> 5;
+        const uint32_t first_dyn = gridDim.x * (kBlock / 32) * d.tiles;        // tiles beyond the statically assigned ones
+        uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
+        while (tile0 < n_tiles) {
+            uint32_t next = 0xFFFFFFFFu;
+            if (first_dyn < n_tiles && (threadIdx.x & 31u) == 0u) next = first_dyn + atomicAdd(&ctl->tile_next, d.tiles);
+            for (uint32_t t = 0; t < d.tiles; ++t)
+                lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+            tile0 = __shfl_sync(0xffffffffu, next, 0);
+        }
         q.drain(d, acc, step & 1u);
         if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
     }
@@ -637,9 +648,16 @@ struct Engine : EngineBase {
         // tiles per warp: large partitions run several tiles per warp (fewer partial queue flushes and block epilogues),
         // small ones keep one so that every SM gets work.  TWB200_TILES overrides.
         // (measured on B200: c4 1M LPs 5.18 -> 5.53 G ev/s and c5 256K LPs 2.53 -> 2.77 with two tiles, 64K LPs slower)
-        d.tiles = nl >= (size_t)prop.multiProcessorCount * TW_MINBLOCKS * kBlock * 2 ? 2u : 1u;
+        // (with persistent warps -- see k_step -- the queue is carried over all tiles of a warp anyway: one tile per grab,
+        // c4 6.12 against 5.99 G ev/s with two, profiles/r2_tuning.md)
+        d.tiles = 1u;
         if (const char *e = getenv("TWB200_TILES")) { const long v = atol(e); if (v >= 1 && v <= 64) d.tiles = (uint32_t)v; }
         step_grid = (int)((nl + (size_t)kBlock * d.tiles - 1) / ((size_t)kBlock * d.tiles));
+        {   // persistent warps: at most the resident blocks of the device (TWB200_STATIC_TILES=1: one block per tile group)
+            int resident = prop.multiProcessorCount * TW_MINBLOCKS;
+            if (const char *e = getenv("TWB200_GRID_BLOCKS_PER_SM")) { const long v = atol(e); if (v >= 1 && v <= 32) resident = prop.multiProcessorCount * (int)v; }
+            if (!getenv("TWB200_STATIC_TILES") && step_grid > resident) step_grid = resident;
+        }
         TW_CUDA(cudaFuncSetAttribute(k_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
         // Keep the per-LP metadata resident in L2 with a persisting access-policy window (kernel nodes captured from
         // this stream inherit it).  TWB200_L2_WINDOW_MB overrides the size (0 = off); default = the inbox counters.

@@ -138,7 +138,8 @@ struct Ctl {                     // device-resident control block
     unsigned long long pend_min; // ordered bits, atomicMin target
     unsigned long long emit_min;
     uint32_t step, finished, error, err_lp;
-    uint32_t done_blocks, pad;
+    uint32_t done_blocks;
+    uint32_t tile_next;          // k_step: next tile of 32 LPs to hand out (warps fetch tiles until none is left)
     unsigned long long c_exec, c_rb_events, c_rollbacks, c_strag, c_anti, c_annih, c_retry,
                        c_sent_local, c_sent_remote, c_fossil, c_steps;   // order == enum in engine.cu
     double   gvt_cap;            // GlobalTimeMessage of an external Time Server: gvt never exceeds it (+inf = none)
