@@ -62,7 +62,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
 }
 
-enum { C_EXEC = 0, C_RB, C_ROLLBACKS, C_STRAG, C_ANTI, C_ANNIH, C_RETRY, C_SLOCAL, C_SREMOTE, C_FOSSIL, C_COUNT };
+enum { C_EXEC = 0, C_RB, C_ROLLBACKS, C_STRAG, C_ANTI, C_ANNIH, C_RETRY, C_SLOCAL, C_SREMOTE, C_FOSSIL, C_LONG, C_COUNT };
 
 // Cross-GPU GVT, run by one warp: every rank publishes its local minimum for step `tag` -- and the number of messages it
 // staged for that peer during the step -- into the mailbox of every peer (NVLink peer stores) and waits until all `world`
@@ -132,7 +132,7 @@ __device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, ui
     unsigned long long p = warp_min_u64(ordered_bits(acc.pend_min));
     unsigned long long e = warp_min_u64(ordered_bits(acc.emit_min));
     const uint32_t vals[C_COUNT] = {acc.exec, acc.rb_events, acc.rollbacks, acc.strag, acc.anti, acc.annih,
-                                    acc.retry, acc.sent_local, acc.sent_remote, acc.fossil};
+                                    acc.retry, acc.sent_local, acc.sent_remote, acc.fossil, acc.long_lanes};
 #pragma unroll
     for (int i = 0; i < C_COUNT; ++i) {
         const unsigned int s = __reduce_add_sync(0xffffffffu, vals[i]);
@@ -178,18 +178,19 @@ __device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, ui
     }
 }
 
-template <class M>
+template <class M, bool kBulk>
 __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_constant__ Dev<M> d)
 {
     Ctl *ctl = d.ctl;
-    const double gvt = *(volatile double *)&ctl->gvt;
+    const uint4 head = __ldcg(reinterpret_cast<const uint4 *>(ctl));          // gvt | step | error in one load (L2: written by the last launch)
+    const double gvt = __hiloint2double((int)head.y, (int)head.x);
     if (!(gvt <= d.stop)) return;                 // GVT passed the stop time: the run is complete (same answer in every block)
-    const uint32_t step = *(volatile uint32_t *)&ctl->step;
+    const uint32_t step = head.z;
     Acc acc; acc.init();
     // An error recorded by an EARLIER launch: nothing to do.  The error word can also be set by a block of THIS launch
     // while later blocks are still being scheduled; those must still take their ticket in block_finish, or no block would
     // be the last one and neither the step counter nor (multi-GPU) the abort tag would be published.
-    if (*(volatile uint32_t *)&ctl->error == 0u) {
+    if (head.w == 0u) {
         double wend = d.stop;
         if (d.horizon >= 0.0) { const double w = gvt + d.horizon; wend = w < wend ? w : wend; }
         extern __shared__ uint4 tw_queue_smem[];             // per warp: work queue + held messages (tw_core.cuh, WorkQ)
@@ -207,11 +208,15 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
             uint32_t next = 0xFFFFFFFFu;
             if (first_dyn < n_tiles && (threadIdx.x & 31u) == 0u) next = first_dyn + atomicAdd(&ctl->tile_next, d.tiles);
             for (uint32_t t = 0; t < d.tiles; ++t)
-                lp_step<M>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+                lp_step<M, kBulk>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
             tile0 = __shfl_sync(0xffffffffu, next, 0);
         }
         q.drain(d, acc, step & 1u);
-        if (d.world > 1) __threadfence_system();      // peer stores must be performed before the cross-GPU reduction
+        // peer stores must be performed before the cross-GPU reduction publishes this step's tag
+        if (d.world > 1) {
+            if (d.flags & kFlagFenceGpu) __threadfence();
+            else if (!(d.flags & kFlagFenceNone)) __threadfence_system();
+        }
     }
     block_finish<M>(d, acc, step);
 }
@@ -222,18 +227,25 @@ template <class M>
 __global__ void __launch_bounds__(kBlock) k_deliver(const __grid_constant__ Dev<M> d)
 {
     Ctl *ctl = d.ctl;
-    if (*(volatile uint32_t *)&ctl->error) return;
-    const uint32_t step = *(volatile uint32_t *)&ctl->step;
+    const uint4 head = __ldcg(reinterpret_cast<const uint4 *>(ctl));          // gvt | step | error
+    if (head.w) return;
+    const uint32_t step = head.z;
     const uint32_t par_prev = (step & 1u) ^ 1u;
+    // the counts: ONE thread per sender and block reads the mailbox (every warp polling the same few words made this
+    // kernel cost 45 us on eight GPUs -- one L2 slice served 150K identical requests), the block shares them
     const GvtSlot *mine = d.peer_slots[d.rank] + (step & 1u) * kMaxWorld;
-    uint32_t cnt[kMaxWorld]; uint32_t total = 0;
-#pragma unroll
-    for (uint32_t r = 0; r < (uint32_t)kMaxWorld; ++r) {
+    __shared__ uint32_t s_cnt[kMaxWorld];
+    if (threadIdx.x < (uint32_t)kMaxWorld) {
+        const uint32_t r = threadIdx.x;
         uint32_t c = 0;
         if (r < d.world && r != d.rank && *(volatile const uint32_t *)&mine[r].tag == step) c = *(volatile const uint32_t *)&mine[r].count;
         if (c > d.stage_cap) c = d.stage_cap;         // the sender has flagged the overflow; never read past the ring
-        cnt[r] = c; total += c;
+        s_cnt[r] = c;
     }
+    __syncthreads();
+    uint32_t cnt[kMaxWorld]; uint32_t total = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < (uint32_t)kMaxWorld; ++r) { cnt[r] = s_cnt[r]; total += cnt[r]; }
     Acc acc; acc.init();
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < total; i += gridDim.x * kBlock) {
         uint32_t j = i, src = 0;
@@ -270,7 +282,7 @@ __global__ void __launch_bounds__(32) k_run_groups(const __grid_constant__ Dev<M
     if (mine && lane == base_lane) d.grp_gvt[grp] = ordered_bits(graw);
     // totals: counters, the partition's local time = minimum over its groups, the round count of the slowest warp
     const uint32_t vals[C_COUNT] = {acc.exec, acc.rb_events, acc.rollbacks, acc.strag, acc.anti, acc.annih,
-                                    acc.retry, acc.sent_local, acc.sent_remote, acc.fossil};
+                                    acc.retry, acc.sent_local, acc.sent_remote, acc.fossil, acc.long_lanes};
 #pragma unroll
     for (int i = 0; i < C_COUNT; ++i) {
         const unsigned int s = __reduce_add_sync(0xffffffffu, vals[i]);
@@ -559,8 +571,9 @@ struct Engine : EngineBase {
     tw_event *d_stage = nullptr; size_t stage_cap = 0;
     unsigned long long *d_tmp = nullptr;  // [2]
     unsigned long long *d_stats = nullptr; // per-LP result staging (tw_read_lp_stats), allocated on first use
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph = nullptr, graph_bulk = nullptr;      // super-steps with / without the bulk selection compiled in
     uint32_t graph_steps = 0; double graph_stop = 0.0;
+    int bulk_mode = -1;                                           // TWB200_BULK=0/1 forces a build; -1: follow the workload
     void *comm = nullptr;                 // ncclComm_t
     std::vector<void *> peer_ptrs;        // opened IPC mappings
     uint64_t launches = 0;
@@ -602,7 +615,8 @@ struct Engine : EngineBase {
         d.stop = p.stop_time;
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);
-        d.flags = p.flags;
+        d.flags = p.flags & 0xFFFFu;
+        if (const char *e = getenv("TWB200_FENCE")) { if (!strcmp(e, "gpu")) d.flags |= kFlagFenceGpu; else if (!strcmp(e, "none")) d.flags |= kFlagFenceNone; }
         {
             double ms = p.sync_timeout_ms ? (double)p.sync_timeout_ms : 20000.0;   // a peer that stays away this long is gone
             if (const char *e = getenv("TWB200_PEER_TIMEOUT_MS")) { const double v = atof(e); if (v > 0.0) ms = v; }
@@ -658,7 +672,9 @@ struct Engine : EngineBase {
             if (const char *e = getenv("TWB200_GRID_BLOCKS_PER_SM")) { const long v = atol(e); if (v >= 1 && v <= 32) resident = prop.multiProcessorCount * (int)v; }
             if (!getenv("TWB200_STATIC_TILES") && step_grid > resident) step_grid = resident;
         }
-        TW_CUDA(cudaFuncSetAttribute(k_step<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
+        TW_CUDA(cudaFuncSetAttribute(k_step<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
+        TW_CUDA(cudaFuncSetAttribute(k_step<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes()));
+        if (const char *e = getenv("TWB200_BULK")) bulk_mode = atoi(e) ? 1 : 0;
         // Keep the per-LP metadata resident in L2 with a persisting access-policy window (kernel nodes captured from
         // this stream inherit it).  TWB200_L2_WINDOW_MB overrides the size (0 = off); default = the inbox counters.
         {
@@ -727,7 +743,14 @@ struct Engine : EngineBase {
         }
         TW_CUDA(cudaMalloc(&d_peer_slots, kMaxWorld * sizeof(GvtSlot *)));
         TW_CUDA(cudaMemcpy(d_peer_slots, d.peer_slots, kMaxWorld * sizeof(GvtSlot *), cudaMemcpyHostToDevice));
-        deliver_grid = 148 * 4;
+        // k_deliver: one staged message per thread for the usual step (a 1M-LP c4 run stages ~250K messages per GPU and
+        // step at 2 GPUs, ~110K at 8); the grid-stride loop takes whatever is beyond.  TWB200_DELIVER_BLOCKS_PER_SM overrides.
+        {
+            cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
+            int per_sm = 16;
+            if (const char *e = getenv("TWB200_DELIVER_BLOCKS_PER_SM")) { const long v = atol(e); if (v >= 1 && v <= 64) per_sm = (int)v; }
+            deliver_grid = prop.multiProcessorCount * per_sm;
+        }
         // one rank per GPU: the mailbox exchange spins on peers, two ranks sharing a GPU could starve each other
         {
             int dev = 0; cudaGetDevice(&dev);
@@ -818,16 +841,20 @@ struct Engine : EngineBase {
         // as neither changes (a bench or a Time Server loop calls tw_run many times with the same stop time)
         if (graph && graph_steps == steps && graph_stop == d.stop) return TW_OK;
         if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
-        cudaGraph_t g = nullptr;
-        TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        for (uint32_t i = 0; i < steps; ++i) {
-            if (P.world > 1) k_deliver<M><<<deliver_grid, kBlock, 0, stream>>>(d);        // what the peers staged in the last step
-            k_step<M><<<step_grid, kBlock, stage_bytes(), stream>>>(d);
-            if (P.world > 1 && !d.fused_gvt) k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.stage_cnt, d.rank, d.world, d.peer_timeout_ns);
+        if (graph_bulk) { cudaGraphExecDestroy(graph_bulk); graph_bulk = nullptr; }
+        for (int bulk = 0; bulk < 2; ++bulk) {
+            cudaGraph_t g = nullptr;
+            TW_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            for (uint32_t i = 0; i < steps; ++i) {
+                if (P.world > 1) k_deliver<M><<<deliver_grid, kBlock, 0, stream>>>(d);        // what the peers staged in the last step
+                if (bulk) k_step<M, true><<<step_grid, kBlock, stage_bytes(), stream>>>(d);
+                else k_step<M, false><<<step_grid, kBlock, stage_bytes(), stream>>>(d);
+                if (P.world > 1 && !d.fused_gvt) k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.stage_cnt, d.rank, d.world, d.peer_timeout_ns);
+            }
+            TW_CUDA(cudaStreamEndCapture(stream, &g));
+            TW_CUDA(cudaGraphInstantiate(bulk ? &graph_bulk : &graph, g, 0));
+            TW_CUDA(cudaGraphDestroy(g));
         }
-        TW_CUDA(cudaStreamEndCapture(stream, &g));
-        TW_CUDA(cudaGraphInstantiate(&graph, g, 0));
-        TW_CUDA(cudaGraphDestroy(g));
         graph_steps = steps; graph_stop = d.stop;
         return TW_OK;
     }
@@ -875,7 +902,7 @@ struct Engine : EngineBase {
             TW_CUDA(cudaEventRecord(e[0], stream));
             if (P.world > 1) { k_deliver<M><<<deliver_grid, kBlock, 0, stream>>>(d); count(1); }
             TW_CUDA(cudaEventRecord(e[1], stream));
-            k_step<M><<<step_grid, kBlock, stage_bytes(), stream>>>(d); count(1);
+            k_step<M, false><<<step_grid, kBlock, stage_bytes(), stream>>>(d); count(1);
             if (P.world > 1 && !d.fused_gvt) { k_gvt_exchange<<<1, 32, 0, stream>>>(d.ctl, d_peer_slots, d.stage_cnt, d.rank, d.world, d.peer_timeout_ns); count(1); }
             TW_CUDA(cudaEventRecord(e[2], stream));
             TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
@@ -909,13 +936,16 @@ struct Engine : EngineBase {
         const uint64_t launches0 = launches;
         TW_CUDA(cudaEventRecord(ev0, stream));
         // pipelined: batch k+1 is enqueued before batch k's control block is inspected
-        int slot = 0; bool pending[2] = {false, false};
+        int slot = 0; bool pending[2] = {false, false}; bool long_seen = false;
         double last_gvt = c0.gvt; uint64_t stall = 0; int result = TW_OK; bool finished = !(c0.gvt <= until);
         Ctl last = c0;
         if (group_kernel) { if constexpr (M::kGroup > 1) result = run_groups(until, c0, last, finished); }
         else if (getenv("TWB200_TIME_KERNELS")) result = run_timed(until, last, finished);
         else while (!finished) {
-            TW_CUDA(cudaGraphLaunch(graph, stream)); count(launches_per_graph(B));
+            // long pending regions (hot LPs of a skewed workload) in the last inspected batch: the build with the
+            // cooperative bulk selection; otherwise the leaner one (either is correct for any state)
+            const bool use_bulk = bulk_mode >= 0 ? bulk_mode == 1 : long_seen;
+            TW_CUDA(cudaGraphLaunch(use_bulk ? graph_bulk : graph, stream)); count(launches_per_graph(B));
             TW_CUDA(cudaMemcpyAsync(&h_ctl[slot], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
             TW_CUDA(cudaEventRecord(ev_chk[slot], stream));
             pending[slot] = true;
@@ -923,6 +953,7 @@ struct Engine : EngineBase {
             if (pending[other]) {
                 TW_CUDA(cudaEventSynchronize(ev_chk[other]));
                 pending[other] = false;
+                long_seen = h_ctl[other].c_long - last.c_long >= (unsigned long long)B;      // at least one such LP per step
                 last = h_ctl[other];
                 post_monitor(last);
                 if ((result = check_device_error(last)) != TW_OK) break;
@@ -1047,6 +1078,7 @@ struct Engine : EngineBase {
         monitor_stop();
         if (stream) cudaStreamSynchronize(stream);
         if (graph) cudaGraphExecDestroy(graph);
+        if (graph_bulk) cudaGraphExecDestroy(graph_bulk);
         for (void *p : peer_ptrs) cudaIpcCloseMemHandle(p);
         if (comm) g_nccl.CommDestroy(comm);
         cudaFree(d.pages); cudaFree(d.saved); cudaFree(meta); cudaFree(d.ctl);

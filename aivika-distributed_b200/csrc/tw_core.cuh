@@ -132,16 +132,17 @@ TW_HD unsigned long long load_inbox_word(const LPIn *p)
 struct alignas(16) GvtSlot { double value; uint32_t tag; uint32_t count; };
 constexpr uint32_t kSlotEmpty = 0xFFFFFFFEu, kSlotAbort = 0xFFFFFFFFu;
 
-struct Ctl {                     // device-resident control block
+struct alignas(16) Ctl {         // device-resident control block
     double   gvt;                // GVT the next step uses (queueGlobalTime)
+    uint32_t step, error;        // (gvt, step, error: the 16 bytes every warp reads at the start of a super-step -- one load)
     double   gvt_local;          // this partition's min before the cross-GPU reduction
     unsigned long long pend_min; // ordered bits, atomicMin target
     unsigned long long emit_min;
-    uint32_t step, finished, error, err_lp;
+    uint32_t finished, err_lp;
     uint32_t done_blocks;
     uint32_t tile_next;          // k_step: next tile of 32 LPs to hand out (warps fetch tiles until none is left)
     unsigned long long c_exec, c_rb_events, c_rollbacks, c_strag, c_anti, c_annih, c_retry,
-                       c_sent_local, c_sent_remote, c_fossil, c_steps;   // order == enum in engine.cu
+                       c_sent_local, c_sent_remote, c_fossil, c_long, c_steps;   // order == enum in engine.cu
     double   gvt_cap;            // GlobalTimeMessage of an external Time Server: gvt never exceeds it (+inf = none)
     unsigned long long c_skipped; // host-injected messages older than GVT that were skipped (dioAllowSkippingOutdatedMessage)
     unsigned long long c_rounds;  // closed-group kernel: rounds of the slowest warp, summed over launches
@@ -151,11 +152,12 @@ struct Ctl {                     // device-resident control block
 struct Acc {
     double pend_min, emit_min;
     uint32_t exec, rb_events, rollbacks, strag, anti, annih, retry, sent_local, sent_remote, fossil;
+    uint32_t long_lanes;             // LPs that started the step with more than 8 * kMaskBits pending entries
     uint32_t err, err_lp;
     TW_HD void init()
     {
         pend_min = pos_inf(); emit_min = pos_inf();
-        exec = rb_events = rollbacks = strag = anti = annih = retry = sent_local = sent_remote = fossil = 0;
+        exec = rb_events = rollbacks = strag = anti = annih = retry = sent_local = sent_remote = fossil = long_lanes = 0;
         err = 0; err_lp = 0;
     }
     TW_HD void fail(uint32_t code, uint32_t lp) { if (!err) { err = code; err_lp = lp; } }
@@ -163,7 +165,7 @@ struct Acc {
     {
         pend_min = dmin(pend_min, o.pend_min); emit_min = dmin(emit_min, o.emit_min);
         exec += o.exec; rb_events += o.rb_events; rollbacks += o.rollbacks; strag += o.strag; anti += o.anti; annih += o.annih;
-        retry += o.retry; sent_local += o.sent_local; sent_remote += o.sent_remote; fossil += o.fossil;
+        retry += o.retry; sent_local += o.sent_local; sent_remote += o.sent_remote; fossil += o.fossil; long_lanes += o.long_lanes;
         if (!err && o.err) { err = o.err; err_lp = o.err_lp; }
     }
 };
@@ -171,6 +173,8 @@ struct Acc {
 constexpr uint32_t kCntStride = 32;          // staging counters sit 128 bytes apart (one L2 line each: no false contention)
 constexpr uint32_t kFlagSkipOutdated = 1u;   // tw_params.flags bit 0: dioAllowSkippingOutdatedMessage (Internal/DIO.hs:96-98)
 constexpr uint32_t kFlagNoGroupKernel = 2u;  // tw_params.flags bit 1: run closed-group models through k_step as well
+constexpr uint32_t kFlagFenceGpu = 1u << 16; // engine-internal (TWB200_FENCE=gpu|none): scope of the per-thread fence after a
+constexpr uint32_t kFlagFenceNone = 1u << 17; // multi-GPU super-step's peer stores (default: system)
 
 template <class M>
 struct Dev {                     // passed to kernels by value
@@ -476,11 +480,21 @@ TW_NOINLINE void drain_slow(const Dev<M> &d, Acc &acc, StepCtx<M> &c, uint32_t l
             // least one step after its twin, and there is at most one live copy there.  The arrivals of this step are
             // no candidates: the copy re-sent by the rolled-back sender can carry the same identity (counter, times) with
             // a different payload and, the deliveries of one flush being unordered, may sit in front of the anti-message.
+            // (the receive times of eight records are fetched together: on a hot LP the region holds a thousand records,
+            // and one dependent load per record made a single anti-message cost hundreds of microseconds)
             uint32_t b = c.consumed0; bool found = false;
-            while (b != head) {
-                --b;
-                const Event m = pg[b & mask];
-                if (!(m.ctr & (kAntiBit | kDeadBit)) && same_message(m, e)) { found = true; break; }
+            while (b != head && !found) {
+                const uint32_t nb = b - head < 8u ? b - head : 8u;
+                double ts8[8];
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) ts8[u] = u < nb ? pg[(b - 1u - u) & mask].recv_ts : neg_inf();
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; ++u) {
+                    if (found || u >= nb || ts8[u] != e.recv_ts) continue;
+                    const Event m = pg[(b - 1u - u) & mask];
+                    if (!(m.ctr & (kAntiBit | kDeadBit)) && same_message(m, e)) { found = true; b = b - 1u - u; }
+                }
+                if (!found) b -= nb;
             }
             if (!found) { fail_checked<M>(d, acc, TW_ERR_ANTI_UNMATCHED, l, c.head_prev); c.live = false; return; }
             const uint32_t rel = b - head;
@@ -510,12 +524,19 @@ TW_NOINLINE uint32_t compact_slow(const Dev<M> &d, Acc &acc, uint32_t l, uint32_
     typename M::State *sv = d.saved + (size_t)l * d.cap;
     const uint32_t pb = head + nproc;
     uint32_t w = pb;
-    for (uint32_t a = pb; a != consumed; ++a) {
-        const Event e = pg[a & mask];
-        if (e.ctr & kDeadBit) {
-            if (a != w) { pg[a & mask] = pg[w & mask]; pg[w & mask] = e; }
+    for (uint32_t a0 = pb; a0 != consumed; ) {                 // (the flag words of eight records are fetched together)
+        const uint32_t nb = consumed - a0 < 8u ? consumed - a0 : 8u;
+        uint64_t c8[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; ++u) c8[u] = u < nb ? pg[(a0 + u) & mask].ctr : 0ull;
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; ++u) {
+            if (u >= nb || !(c8[u] & kDeadBit)) continue;
+            const uint32_t a = a0 + u;
+            if (a != w) { const Event e = pg[a & mask]; pg[a & mask] = pg[w & mask]; pg[w & mask] = e; }
             ++w;
         }
+        a0 += nb;
     }
     const uint32_t k = w - pb;
     if (k) {
@@ -607,11 +628,131 @@ __device__ __forceinline__ void coop_min(const typename M::Event *lpg, uint32_t 
     const unsigned w2 = __ballot_sync(0xffffffffu, bs == ms && bsrc == msrc && bc == mc && bs != ~0ull);
     ix_out = __shfl_sync(0xffffffffu, bix, w2 ? __ffs((int)w2) - 1 : 0);    // identical keys (twins): any of them
 }
+
+// Cooperative bulk selection for a long pending region (hot LPs of a skewed workload hold a thousand pending events and
+// execute dozens of them per super-step; one whole-region search per event made that quadratic).  The warp selects up to
+// `want` (<= 32) of the earliest in-window records of the leader's region in ONE pass and moves them, in order, to the
+// front of the region, where the owner then executes them one after the other without any further search.
+//   pass 1   every lane keeps the four smallest keys of its strided share of the region.  A key is (receive time
+//            quantised to 32 bits over [gvt, limit]) << 32 | position: one 64-bit min/max per comparison.
+//   merge    four bitonic sort + merge rounds over the lanes leave the 32 smallest of those 128 keys, sorted, one per lane.
+//   validity everything below `bound` -- the smallest key a lane had to drop, or that fell out of a merge -- is certainly
+//            among them; the sorted prefix below it is exact.  Two neighbours with the same time quantum (or the bound in
+//            the quantum of the last one) need the full key: the prefix ends before them; if it is empty, the caller does
+//            one exact whole-region search (coop_min) and comes back.
+//   move     the m selected records go to positions 0..m-1; the records they displace go to the vacated positions.
+// All lanes call it with the leader's arguments.  Returns m; rest_out = lower bound of the receive times of everything
+// that is still pending behind those m records, in_window_left = whether any of it lies inside the window.
+template <class M>
+TW_NOINLINE uint32_t coop_select(typename M::Event *lpg, uint32_t mask, uint32_t beg, uint32_t n, uint64_t gbits,
+                                                uint64_t lbits, uint32_t want, double &rest_out, bool &in_window_left)
+{
+    using Event = typename M::Event;
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr unsigned long long kNone = ~0ull;
+    uint32_t qs = 0;                                            // (lbits - gbits) >> qs < 2^32 - 1
+    { const uint64_t R = lbits - gbits; const uint32_t len = bitlen64(R); qs = len > 32u ? len - 32u : 0u; if ((R >> qs) >= 0xFFFFFFFFull) ++qs; }
+    unsigned long long c0 = kNone, c1 = kNone, c2 = kNone, c3 = kNone, bound = kNone;   // this lane's four smallest keys; smallest dropped
+    uint64_t oow = ~0ull;                                       // earliest record beyond the window (exact bits)
+    for (uint32_t k = lane; k < n; k += 128u) {
+        uint64_t tb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t kk = k + 32u * (uint32_t)u;
+            tb[u] = kk < n ? d2bits(lpg[(beg + kk) & mask].recv_ts) : ~0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t kk = k + 32u * (uint32_t)u;
+            const bool in = tb[u] <= lbits;
+            oow = (!in && tb[u] < oow) ? tb[u] : oow;
+            unsigned long long cur = in ? (((tb[u] - gbits) >> qs) << 32) | kk : kNone;
+            unsigned long long lo;
+            lo = cur < c0 ? cur : c0; cur = cur < c0 ? c0 : cur; c0 = lo;
+            lo = cur < c1 ? cur : c1; cur = cur < c1 ? c1 : cur; c1 = lo;
+            lo = cur < c2 ? cur : c2; cur = cur < c2 ? c2 : cur; c2 = lo;
+            lo = cur < c3 ? cur : c3; cur = cur < c3 ? c3 : cur; c3 = lo;
+            bound = cur < bound ? cur : bound;
+        }
+    }
+    // the 32 smallest of the 4 x 32 kept keys, ascending over the lanes
+    unsigned long long best = kNone;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        unsigned long long v = r == 0 ? c0 : r == 1 ? c1 : r == 2 ? c2 : c3;
+#pragma unroll
+        for (uint32_t kk = 2; kk <= 32u; kk <<= 1)               // bitonic sort across the lanes
+#pragma unroll
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, (int)j);
+                const bool take_min = ((lane & j) == 0u) == ((lane & kk) == 0u);
+                v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+            }
+        if (r == 0) { best = v; continue; }
+        // merge: lane i keeps the smaller of best[i] and v[31 - i]; what falls out bounds the rest
+        const unsigned long long o = __shfl_sync(0xffffffffu, v, (int)(31u - lane));
+        const unsigned long long out = o < best ? best : o;
+        best = o < best ? o : best;
+        bound = out < bound ? out : bound;
+#pragma unroll
+        for (uint32_t j = 16; j > 0; j >>= 1) {                 // the result is bitonic: five more stages sort it
+            const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, best, (int)j);
+            best = ((lane & j) == 0u) ? (o2 < best ? o2 : best) : (o2 > best ? o2 : best);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, bound, o); bound = t < bound ? t : bound; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(0xffffffffu, oow, o); oow = t < oow ? t : oow; }
+    // the exact prefix: below the bound, and no two neighbours (nor the last one and the bound) in one time quantum
+    const unsigned long long nxt = __shfl_sync(0xffffffffu, best, (int)((lane + 1u) & 31u));
+    const unsigned long long after = lane == 31u ? bound : (nxt < bound ? nxt : bound);     // the smallest key behind this one
+    const bool ok = best != kNone && lane < want && best < bound && (best >> 32) != (after >> 32);
+    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+    const uint32_t m = okm == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okm) - 1u;          // leading run of ok lanes
+    // what stays pending behind the prefix: the next key (or the bound), and the records beyond the window
+    unsigned long long restk = bound;
+    { const unsigned long long bm = __shfl_sync(0xffffffffu, best, (int)(m & 31u)); if (m < 32u && bm < restk) restk = bm; }
+    in_window_left = restk != kNone;
+    double rest = pos_inf();
+    if (restk != kNone) rest = bits2d(gbits + ((restk >> 32) << qs));
+    if (oow != ~0ull) rest = dmin(rest, bits2d(oow));
+    rest_out = rest;
+    if (m == 0u) return 0u;
+    // move: selected record i -> position i; the records displaced from the first m positions -> the vacated positions
+    const bool sel = lane < m;
+    const uint32_t pos = (uint32_t)best;
+    unsigned lowsel = (sel && pos < m) ? (1u << pos) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lowsel |= __shfl_xor_sync(0xffffffffu, lowsel, o);
+    const bool disp = lane < m && !((lowsel >> lane) & 1u);
+    const unsigned dmask = __ballot_sync(0xffffffffu, disp);
+    const unsigned hmask = __ballot_sync(0xffffffffu, sel && pos >= m);     // as many holes as displaced records
+    Event rs, rd;
+    if (sel) rs = lpg[(beg + pos) & mask];
+    if (disp) rd = lpg[(beg + lane) & mask];
+    uint32_t hl = 0;                                            // the lane that selected this lane's hole
+    if (disp) {
+        uint32_t k = (uint32_t)__popc(dmask & ((1u << lane) - 1u));
+        unsigned hmm = hmask;
+        while (k--) hmm &= hmm - 1u;
+        hl = (uint32_t)__ffs((int)hmm) - 1u;
+    }
+    const uint32_t hp = __shfl_sync(0xffffffffu, pos, (int)(hl & 31u));
+    __syncwarp();
+    if (sel) lpg[(beg + lane) & mask] = rs;
+    if (disp) lpg[(beg + hp) & mask] = rd;
+    __syncwarp();
+    return m;
+}
 #endif
 
 // The super-step of LP `l` (local index).  `gvt` is the GVT of this step, `wend` the end of the optimistic window,
 // `step` the super-step number.  Must be called by every lane of the warp (lanes with l >= n_local pass through idle).
-template <class M>
+// kBulk: compile the cooperative bulk selection for long pending regions in (coop_select).  The engine keeps two builds
+// of k_step and runs the one with it only while the partition has such regions: the extra state costs the common path
+// registers (c4 6.0 -> 5.3 G ev/s when it is always compiled in).
+template <class M, bool kBulk = true>
 TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gvt, double wend, uint32_t step)
 {
     const uint32_t parity = step & 1u;
@@ -769,7 +910,11 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             nproc = rlow;
             h.lvt = rlow > 0 ? pg[(head + rlow - 1) & mask].recv_ts : neg_inf();
         }
-        if (live && consumed - head >= (d.cap >> 1)) {
+        // (a ring that is half full is not necessarily full of tombstones -- a hot LP of a skewed workload simply has that
+        // many pending events --, and the pass reads every pending record: every 16th step, and at once above seven
+        // eighths.  Not rarer: tombstones that stay are "executed" as no-ops and use up the LP's batch -- c5 needed 576
+        // instead of 545 super-steps with the pass only above three quarters)
+        if (live && consumed - head >= (d.cap >> 1) && ((step & 15u) == 0u || consumed - head >= d.cap - (d.cap >> 3))) {
             Acc sacc; sacc.init();
             head = compact_slow<M>(d, sacc, l, head, nproc, consumed);
             acc.merge(sacc);
@@ -801,6 +946,13 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
         if ((R >> qshift) >= ((1ull << kQuantBits) - 1ull)) ++qshift;
     }
     bool heavy = live && (nreg > kMaskBits || exact_only);  // exact search over the whole region, no candidate list
+    // long regions on the GPU: up to 32 events at a time are selected and lined up by the whole warp (coop_select)
+    const bool bulk = kBulk && TW_SIMT && heavy && !exact_only;
+    // (tells the host which build of k_step to launch next: a few dozen entries over the list's reach -- a c4 run has some
+    // hundred such LPs in every step -- are handled well enough by the per-event search; hundreds of entries are not)
+    if (live && nreg > 8u * kMaskBits) acc.long_lanes++;
+    bool exact_once = false;                                 // bulk lane: the front of the region is tied, one exact search
+    double bulk_rest = pos_inf();                            // bulk lane: lower bound of what the last selection left behind
     double rest_min = pos_inf();
     uint32_t done = 0;                                       // events executed in this step
     bool stopped = !live;                                    // no further execution by this lane in this step
@@ -811,6 +963,8 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     for (int i = 0; i < kCand; ++i) c[i] = kNoCand;
     uint32_t drop = kNoCand;                                 // smallest in-window key that did not fit into the list
     uint32_t nleft = 0;                                      // in-window entries of the current round not yet executed
+    uint32_t &presel = nleft;                                // bulk lane (no candidate list): selected records lined up at the
+                                                             // front of the region, not yet executed -- the same register
     uint32_t rbase = 0, mv = 0;                              // round base (= done at the scan); displaced-entry map
     bool need_scan = live && !heavy;
     const char *pgb = reinterpret_cast<const char *>(pg);
@@ -875,16 +1029,44 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             need_scan = false;
         }
         TW_RECONVERGE();
+#if TW_SIMT
+        // bulk lanes with nothing lined up: the next selection
+        if constexpr (kBulk)
+        for (unsigned bm = __ballot_sync(0xffffffffu, bulk && live && !searched && !exact_once && presel == 0u && !stopped && done < maxb); bm; bm &= bm - 1u) {
+            const int leader = __ffs(bm) - 1;
+            Event *lpg = reinterpret_cast<Event *>(__shfl_sync(0xffffffffu, (unsigned long long)pg, leader));
+            const uint32_t lbeg = __shfl_sync(0xffffffffu, pbeg + done, leader);
+            const uint32_t ln = __shfl_sync(0xffffffffu, nreg - done, leader);
+            const uint32_t lwant = __shfl_sync(0xffffffffu, maxb - done < 32u ? maxb - done : 32u, leader);
+            // (GVT and the window are the leader's: in the closed-group kernel every group of the warp has its own)
+            const uint64_t lg = __shfl_sync(0xffffffffu, (unsigned long long)gbits, leader), ll = __shfl_sync(0xffffffffu, (unsigned long long)lbits, leader);
+            double rest_; bool left_;
+            const uint32_t m = coop_select<M>(lpg, mask, lbeg, ln, lg, ll, lwant, rest_, left_);
+            if ((int)(threadIdx.x & 31u) == leader) {
+                presel = m; bulk_rest = rest_;
+                if (m == 0u) {
+                    if (left_ && !(rest_ > limit)) exact_once = true;            // a tie at the front: settle one event exactly
+                    else { rest_min = dmin(rest_min, rest_); searched = true; }  // nothing (more) inside the window
+                }
+            }
+        }
+#endif
 
         for (;;) {                                           // iterations within the round
             const bool can_exec = !stopped && done < maxb;
+            // a bulk lane that cannot go on reports what it leaves pending: the next lined-up record and the rest
+            if (bulk && live && !searched && !exact_once && !can_exec) {
+                if (presel) bulk_rest = dmin(bulk_rest, pg[(pbeg + done) & mask].recv_ts);
+                rest_min = dmin(rest_min, bulk_rest); searched = true;
+            }
             // a heavy lane keeps searching until it knows the earliest record it leaves pending (its GVT contribution)
-            bool want = heavy ? (live && !searched) : (can_exec && c[0] != kNoCand);
+            const bool lined = bulk && !exact_once;           // executes from the front of its region, no search
+            bool want = heavy ? (live && !searched && (!lined || presel > 0u)) : (can_exec && c[0] != kNoCand);
             if (!warp_any(want)) break;
             uint32_t bix = 0; double bts = pos_inf();
             // heavy lanes: earliest record of [pbeg + done, consumed), found by the whole warp
 #if TW_SIMT
-            for (unsigned hm = __ballot_sync(0xffffffffu, want && heavy); hm; hm &= hm - 1u) {
+            for (unsigned hm = __ballot_sync(0xffffffffu, want && heavy && !lined); hm; hm &= hm - 1u) {
                 const int leader = __ffs(hm) - 1;
                 const Event *lpg = reinterpret_cast<const Event *>(__shfl_sync(0xffffffffu, (unsigned long long)pg, leader));
                 const uint32_t lbeg = __shfl_sync(0xffffffffu, pbeg + done, leader);
@@ -898,7 +1080,10 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
 #endif
             // isEventOverflow analogue (Internal/Event.hs:289-306): with proc_limit processed-but-uncommitted entries
             // only safe events (<= GVT, fossil-collected next) proceed
-            if (want && heavy) {
+            if (want && lined) {
+                bix = done;                                   // the next lined-up record; throttled like any other
+                if (nproc >= d.proc_limit && !(pg[(pbeg + bix) & mask].recv_ts <= gvt)) { stopped = true; want = false; }
+            } else if (want && heavy) {
                 bix += done;
                 const bool throttled = nproc >= d.proc_limit && !(bts <= gvt);
                 if (!(bts <= limit) || !can_exec || throttled) { rest_min = dmin(rest_min, bts); searched = true; want = false; }
@@ -943,6 +1128,8 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
                         if (bix != pi || noop) pg[(pbeg + pi) & mask] = e;
                         if constexpr (!M::kReversible) sv[(pbeg + pi) & mask] = before;
                         nproc++; h.lvt = e.recv_ts; done++;
+                        if (lined) presel--;
+                        exact_once = false;
                         if (!noop) {
                             acc.exec++;
                             if constexpr (M::kSplit) { w = M::make_work(lp, before, e, false); has = true; }
@@ -1021,7 +1208,7 @@ __device__ __forceinline__ bool group_rounds(const Dev<M> &d, Acc &acc, WorkQ<M>
         q.gmin[lane] = ~0ull;
         __syncwarp();
         const uint32_t step = step0 + rounds;
-        lp_step<M>(d, acc, q, l, gvt, wend, step);                        // every group of the warp takes part in every round
+        lp_step<M, false>(d, acc, q, l, gvt, wend, step);                 // every group of the warp takes part in every round
         q.drain(d, acc, step & 1u);
         __syncwarp();
         // the group's GVT: minimum over its lanes of what stays pending, and over the messages its LPs sent
