@@ -28,7 +28,7 @@ ERROR_NAMES = {
 # every symbol include/twb200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
-    "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range",
+    "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range", "tw_populate",
     "tw_attach_time_server", "tw_local_time", "tw_global_time_message", "tw_skipped_outdated",
     "tw_wire_create", "tw_wire_destroy", "tw_wire_encode_message", "tw_wire_decode_message", "tw_wire_encode_lp_message",
     "tw_wire_decode_lp_message", "tw_wire_encode_ts_message", "tw_wire_decode_ts_message", "tw_wire_handle_lp_message",
@@ -130,6 +130,8 @@ def load(path=None):
     lib.tw_global_time_message.argtypes = [H, C.c_double, C.POINTER(C.c_int)]; lib.tw_global_time_message.restype = C.c_int
     lib.tw_skipped_outdated.argtypes = [H, C.POINTER(C.c_uint64)]; lib.tw_skipped_outdated.restype = C.c_int
     lib.tw_partition.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; lib.tw_partition.restype = C.c_int
+    lib.tw_populate.argtypes = [C.c_void_p]
+    lib.tw_populate.restype = C.c_int
     lib.tw_model_initial_events.argtypes = [C.POINTER(tw_params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.tw_model_initial_events.restype = C.c_int
     lib.tw_model_initial_events_range.argtypes = [C.POINTER(tw_params), C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,

@@ -341,6 +341,36 @@ __global__ void __launch_bounds__(kBlock) k_route(const Dev<M> d, const tw_event
     }
 }
 
+// runEventInStartTime on the device: every LP of this partition creates its own start-time events (M::start_event: the
+// PHOLD population, the `machine` processes of the MachRep slaves) and delivers them like host-injected messages -- the
+// synthetic population never crosses PCIe.  One thread per LP.
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_populate(const Dev<M> d, double start_time)
+{
+    Ctl *ctl = d.ctl;
+    const uint32_t step = ctl->step;
+    Acc acc; acc.init();
+    const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
+    if (l < d.n_local) {
+        const uint32_t lp = d.lp_base + l;
+        for (uint32_t j = 0; ; ++j) {
+            tw_event w;
+            if (!M::start_event(d.mp, start_time, lp, j, w)) break;
+            route_event<M>(d, acc, (step & 1u) ^ 1u, w);
+            if (d.grp_gvt) atomicMin(&d.grp_gvt[l / M::kGroup], ordered_bits(w.recv_ts));
+        }
+    }
+    __shared__ unsigned long long s_emit[kBlock / 32];
+    unsigned long long e = warp_min_u64(ordered_bits(acc.emit_min));
+    if ((threadIdx.x & 31) == 0) s_emit[threadIdx.x >> 5] = e;
+    if (acc.err) { if (atomicCAS(&ctl->error, 0u, acc.err) == 0u) ctl->err_lp = acc.err_lp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kBlock / 32; ++w) e = s_emit[w] < e ? s_emit[w] : e;
+        if (e != ordered_bits(pos_inf())) atomicMin(&ctl->emit_min, e);
+    }
+}
+
 // The same exchange as a kernel of its own (TWB200_GVT_KERNEL=1: comparison with the fused form; also the mode to use
 // under ncu or compute-sanitizer, which serialise kernels and would make the fused wait time out).
 __global__ void k_gvt_exchange(Ctl *ctl, GvtSlot *const *peer_slots_dev, uint32_t *stage_cnt, uint32_t rank, uint32_t world,
@@ -476,6 +506,7 @@ struct EngineBase {
     virtual ~EngineBase() {}
     virtual int reset() = 0;
     virtual int enqueue(const tw_event *evs, size_t n) = 0;
+    virtual int populate() = 0;
     virtual int run(double until, tw_run_stats *st) = 0;
     virtual int gvt(double *g) = 0;
     virtual int lp_state(uint32_t lp, tw_lp_state *out) = 0;
@@ -811,6 +842,17 @@ struct Engine : EngineBase {
         TW_CUDA(cudaMemcpyAsync(d_stage, evs, n * sizeof(tw_event), cudaMemcpyHostToDevice, stream));
         size_t blocks = (n + kBlock - 1) / kBlock; if (blocks > 148 * 16) blocks = 148 * 16;
         k_route<M><<<(int)blocks, kBlock, 0, stream>>>(d, d_stage, n);
+        k_fold_inject<<<1, 1, 0, stream>>>(d.ctl); count(2);
+        TW_CUDA(cudaGetLastError());
+        if (P.world > 1) { int rc = barrier_all(); if (rc) return rc; }
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        return check_device_error(h_ctl[0]);
+    }
+
+    int populate() override
+    {
+        k_populate<M><<<grid, kBlock, 0, stream>>>(d, P.start_time);
         k_fold_inject<<<1, 1, 0, stream>>>(d.ctl); count(2);
         TW_CUDA(cudaGetLastError());
         if (P.world > 1) { int rc = barrier_all(); if (rc) return rc; }
@@ -1159,6 +1201,7 @@ int tw_destroy(tw_engine *e) { if (!e) return TW_ERR_INVALID_ARG; delete e->impl
 int tw_reset(tw_engine *e) { return e ? e->impl->reset() : TW_ERR_INVALID_ARG; }
 int tw_enqueue_message(tw_engine *e, const tw_event *ev) { return e ? e->impl->enqueue(ev, 1) : TW_ERR_INVALID_ARG; }
 int tw_enqueue_messages(tw_engine *e, const tw_event *evs, size_t n) { return e ? e->impl->enqueue(evs, n) : TW_ERR_INVALID_ARG; }
+int tw_populate(tw_engine *e) { return e ? e->impl->populate() : TW_ERR_INVALID_ARG; }
 int tw_run(tw_engine *e, double until, tw_run_stats *st) { return e ? e->impl->run(until, st) : TW_ERR_INVALID_ARG; }
 int tw_gvt(tw_engine *e, double *g) { return (e && g) ? e->impl->gvt(g) : TW_ERR_INVALID_ARG; }
 int tw_lp_state_get(tw_engine *e, uint32_t lp, tw_lp_state *out) { return (e && out) ? e->impl->lp_state(lp, out) : TW_ERR_INVALID_ARG; }

@@ -125,19 +125,25 @@ struct PholdModel {
         emit(p, make_work(lp, s, e, false), out, n_out);
         return advance(p, lp, s, e);
     }
+    // The j-th start-time event of LP lp (what the LP's model enqueues from runEventInStartTime); false: it has fewer.
+    TW_HD static bool start_event(const Params &p, double /*start_time*/, uint32_t lp, uint32_t j, tw_event &e)
+    {
+        if (j >= p.population) return false;
+        e.recv_ts = expo_variate(uniform01(stream_draw(lp_stream_key(p.seed, lp), j)), p.mean);
+        e.send_ts = 0.0; e.ctr = j; e.src = lp; e.dst = lp; e.type = 0; e.pad = 0; e.value = 0.0;
+        return true;
+    }
     static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
         Params p = make_params(tp);
         size_t n = 0;
-        for (uint32_t i = lp0; i < p.n_lps && i < lp1; ++i) {
-            const uint64_t key = lp_stream_key(p.seed, i);
-            for (uint32_t j = 0; j < p.population; ++j) {
+        for (uint32_t i = lp0; i < p.n_lps && i < lp1; ++i)
+            for (uint32_t j = 0; ; ++j) {
+                tw_event e;
+                if (!start_event(p, tp.start_time, i, j, e)) break;
                 if (n >= cap) return n;
-                tw_event &e = out[n++];
-                e.recv_ts = expo_variate(uniform01(stream_draw(key, j)), p.mean);
-                e.send_ts = 0.0; e.ctr = j; e.src = i; e.dst = i; e.type = 0; e.pad = 0; e.value = 0.0;
+                out[n++] = e;
             }
-        }
         return n;
     }
 };
@@ -263,15 +269,22 @@ struct MachRepModel {
         o.immed_prop = (double)s.n_immed / (double)s.n_rep;            // :219-224
         return o;
     }
+    TW_HD static bool start_event(const Params &, double start_time, uint32_t lp, uint32_t j, tw_event &e)
+    {
+        if (lp % 3u == 0 || j > 0) return false;               // runEventInStartTime machine, :154 (slaves only)
+        e.recv_ts = start_time; e.send_ts = start_time; e.ctr = 0; e.src = lp; e.dst = lp;
+        e.type = TW_MR_START; e.pad = 0; e.value = 0.0;
+        return true;
+    }
     static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
+        const Params p = make_params(tp);
         size_t n = 0;
         for (uint32_t lp = lp0; lp < tp.n_lps && lp < lp1; ++lp) {
-            if (lp % 3u == 0) continue;                        // runEventInStartTime machine, :154
+            tw_event e;
+            if (!start_event(p, tp.start_time, lp, 0, e)) continue;
             if (n >= cap) return n;
-            tw_event &e = out[n++];
-            e.recv_ts = tp.start_time; e.send_ts = tp.start_time; e.ctr = 0; e.src = lp; e.dst = lp;
-            e.type = TW_MR_START; e.pad = 0; e.value = 0.0;
+            out[n++] = e;
         }
         return n;
     }
@@ -350,15 +363,22 @@ struct MachRep1Model {
         o.immed_prop = 0.0;
         return o;
     }
+    TW_HD static bool start_event(const Params &, double start_time, uint32_t lp, uint32_t j, tw_event &e)
+    {
+        if (lp % 3u == 0 || j > 0) return false;               // runProcessInStartTime machine, :68 (slaves only)
+        e.recv_ts = start_time; e.send_ts = start_time; e.ctr = 0; e.src = lp; e.dst = lp;
+        e.type = TW_M1_START; e.pad = 0; e.value = 0.0;
+        return true;
+    }
     static size_t initial_events(const tw_params &tp, tw_event *out, size_t cap, uint32_t lp0 = 0, uint32_t lp1 = 0xFFFFFFFFu)
     {
+        const Params p = make_params(tp);
         size_t n = 0;
         for (uint32_t lp = lp0; lp < tp.n_lps && lp < lp1; ++lp) {
-            if (lp % 3u == 0) continue;                        // runProcessInStartTime machine, :68
+            tw_event e;
+            if (!start_event(p, tp.start_time, lp, 0, e)) continue;
             if (n >= cap) return n;
-            tw_event &e = out[n++];
-            e.recv_ts = tp.start_time; e.send_ts = tp.start_time; e.ctr = 0; e.src = lp; e.dst = lp;
-            e.type = TW_M1_START; e.pad = 0; e.value = 0.0;
+            out[n++] = e;
         }
         return n;
     }

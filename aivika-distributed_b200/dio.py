@@ -261,6 +261,11 @@ class DIO:
         self._check(rc)
         return buf[: n.value]
 
+    def runEventInStartTime(self):
+        """Every LP enqueues its model's own start-time events on the device (tw_populate): what the reference's programs do
+        with `runEventInStartTime` / `runProcessInStartTime` on each LP.  Equivalent to enqueueMessages(initialEvents())."""
+        self._check(self.lib.tw_populate(self.h))
+
     def enqueueMessages(self, events: np.ndarray):
         """QueueMessageBulk: `events` is a host array of EVENT_DTYPE records."""
         assert events.dtype == EVENT_DTYPE and events.flags["C_CONTIGUOUS"]

@@ -121,6 +121,8 @@ class DIO {
         return ev;
     }
     void enqueueMessages(const std::vector<tw_event> &ev) { check(tw_enqueue_messages(h_, ev.data(), ev.size())); }
+    // runEventInStartTime on every LP, on the device (== enqueueMessages(initialEvents()) without the host buffer)
+    void runEventInStartTime() { check(tw_populate(h_)); }
     // enqueueMessage pid t a
     void enqueueMessage(uint32_t pid, double t, uint32_t src, double send_time, uint64_t ctr = 0, uint32_t type = 0, double value = 0.0)
     {

@@ -187,6 +187,12 @@ int tw_enqueue_message(tw_engine *e, const tw_event *ev);
  * Messages whose dst is owned by another partition are ignored (each rank passes the same buffer or its own slice). */
 int tw_enqueue_messages(tw_engine *e, const tw_event *evs, size_t n);
 
+/* runEventInStartTime (the body every reference program runs on each LP at the start time, e.g. `machine` in
+ * tests/MachRep2DistributedReproducible.hs:154, tests/MachRep1.hs:68; for PHOLD the initial population): every LP of this
+ * partition creates its model's own start-time events ON THE DEVICE.  Same events as tw_model_initial_events_range +
+ * tw_enqueue_messages, without the host buffer and the PCIe copy.  Collective over the ranks of a multi-GPU engine. */
+int tw_populate(tw_engine *e);
+
 /* runEventInStopTime (Internal/Event.hs:124-129, 743-752): advance until GVT passes until_time
  * (the reference returns when its GVT copy equals the stop time, :717-730). */
 int tw_run(tw_engine *e, double until_time, tw_run_stats *stats);

@@ -416,3 +416,26 @@ def test_phold_equal_timestamps(H):
     for n, pop, rp, hz, batch in ((50, 8, 50, 1.0, 4), (2000, 6, 30, -1.0, 4), (64, 5, 100, 0.5, 2), (5000, 8, 50, 0.5, 3)):
         check_phold(H, H.phold_params(n, 3.0, population=pop, remote_pct=rp, lookahead=0.5, mean=0.0, horizon=hz,
                                       batch=batch, cap=512))
+
+
+def test_start_time_events_generated_on_the_device(H):
+    """tw_populate (runEventInStartTime on every LP, on the device): the same committed trace as the host-built start-time
+    messages, for PHOLD (the population) and for both MachRep models (the slaves' `machine` processes), against the oracle."""
+    d = D()
+    p = H.phold_params(3001, 5.0, remote_pct=40, horizon=0.5, batch=6, cap=256, seed=11)
+    o_exec, o_hash, o_sum = H.oracle_phold(p)
+    dio = d.DIO(d.PHOLD(p.n_lps, p.phold.population, p.phold.remote_pct, p.phold.lookahead, p.phold.mean, p.phold.seed),
+                d.DIOParams(dioTimeHorizon=0.5, queueCapacity=256, maxEventsPerStep=6), d.Specs(0.0, 5.0))
+    dio.runEventInStartTime()
+    st = dio.runEventInStopTime()
+    n_exec, h = dio.lpStats()
+    dio.close()
+    assert (n_exec == o_exec).all() and (h == o_hash).all() and st.committed == o_sum.committed
+    for grouped in (True, False):
+        dio = d.DIO(d.MachRep2(64), d.DIOParams(queueCapacity=128, stepsPerLaunch=32, closedGroupKernel=grouped), d.Specs(0.0, 200.0))
+        dio.runEventInStartTime()
+        dio.runEventInStopTime()
+        res = dio.machRepResults()
+        dio.close()
+        ores = H.oracle_machrep(H.machrep_params(64, 200.0))
+        assert all(res[r]["up_time_prop"] == ores[r].up_time_prop and res[r]["immed_prop"] == ores[r].immed_prop for r in range(64))
