@@ -29,7 +29,7 @@ ERROR_NAMES = {
 EXPORTS = [
     "tw_create", "tw_destroy", "tw_reset", "tw_enqueue_message", "tw_enqueue_messages", "tw_run", "tw_gvt",
     "tw_lp_state_get", "tw_read_lp_stats", "tw_read_machrep", "tw_partition", "tw_set_monitor", "tw_model_initial_events", "tw_model_initial_events_range", "tw_populate",
-    "tw_attach_time_server", "tw_local_time", "tw_global_time_message", "tw_skipped_outdated",
+    "tw_attach_time_server", "tw_local_time", "tw_global_time_message", "tw_skipped_outdated", "tw_max_ring_occupancy",
     "tw_wire_create", "tw_wire_destroy", "tw_wire_encode_message", "tw_wire_decode_message", "tw_wire_encode_lp_message",
     "tw_wire_decode_lp_message", "tw_wire_encode_ts_message", "tw_wire_decode_ts_message", "tw_wire_handle_lp_message",
     "tw_nccl_unique_id", "tw_last_error", "tw_strerror", "tw_version", "tw_kernel_launch_count",
@@ -129,6 +129,7 @@ def load(path=None):
     lib.tw_local_time.argtypes = [H, C.POINTER(C.c_double)]; lib.tw_local_time.restype = C.c_int
     lib.tw_global_time_message.argtypes = [H, C.c_double, C.POINTER(C.c_int)]; lib.tw_global_time_message.restype = C.c_int
     lib.tw_skipped_outdated.argtypes = [H, C.POINTER(C.c_uint64)]; lib.tw_skipped_outdated.restype = C.c_int
+    lib.tw_max_ring_occupancy.argtypes = [H, C.POINTER(C.c_uint32)]; lib.tw_max_ring_occupancy.restype = C.c_int
     lib.tw_partition.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]; lib.tw_partition.restype = C.c_int
     lib.tw_populate.argtypes = [C.c_void_p]
     lib.tw_populate.restype = C.c_int

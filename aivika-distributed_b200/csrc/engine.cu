@@ -139,6 +139,7 @@ __device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, ui
         if (lane == 0 && s) atomicAdd(&s_cnt[i], s);
     }
     if (acc.err) { if (atomicCAS(&ctl->error, 0u, acc.err) == 0u) ctl->err_lp = acc.err_lp; }
+    if (acc.max_occ) atomicMax(&ctl->max_occ, acc.max_occ);
     if (lane == 0) { s_pend[warp] = p; s_emit[warp] = e; }
     __syncthreads();
     if (threadIdx.x < C_COUNT) {
@@ -517,6 +518,7 @@ struct EngineBase {
     virtual int global_time_message(double t, int *accepted) = 0;
     virtual int attach_time_server(int on) = 0;
     virtual int skipped_outdated(uint64_t *n) = 0;
+    virtual int max_ring_occupancy(uint32_t *n) = 0;
     // dioSimulationMonitoringAction: the callback runs on a worker thread of its own, never on the thread that launches
     // the super-steps (a slow callback must not delay the launches: other GPUs wait for this one in their mailbox round)
     tw_monitor_fn monitor = nullptr; void *monitor_user = nullptr;
@@ -1107,6 +1109,13 @@ struct Engine : EngineBase {
         return TW_OK;
     }
     int attach_time_server(int on) override { external_time = on != 0; return reset(); }
+    int max_ring_occupancy(uint32_t *n) override
+    {
+        TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
+        TW_CUDA(cudaStreamSynchronize(stream));
+        *n = h_ctl[0].max_occ;
+        return TW_OK;
+    }
     int skipped_outdated(uint64_t *n) override
     {
         TW_CUDA(cudaMemcpyAsync(&h_ctl[0], d.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, stream));
@@ -1215,6 +1224,7 @@ int tw_set_monitor(tw_engine *e, tw_monitor_fn fn, void *user)
     return TW_OK;
 }
 int tw_skipped_outdated(tw_engine *e, uint64_t *n) { return (e && n) ? e->impl->skipped_outdated(n) : TW_ERR_INVALID_ARG; }
+int tw_max_ring_occupancy(tw_engine *e, uint32_t *n) { return (e && n) ? e->impl->max_ring_occupancy(n) : TW_ERR_INVALID_ARG; }
 int tw_attach_time_server(tw_engine *e, int on) { return e ? e->impl->attach_time_server(on) : TW_ERR_INVALID_ARG; }
 int tw_local_time(tw_engine *e, double *t) { return (e && t) ? e->impl->local_time(t) : TW_ERR_INVALID_ARG; }
 int tw_global_time_message(tw_engine *e, double t, int *accepted) { return e ? e->impl->global_time_message(t, accepted) : TW_ERR_INVALID_ARG; }

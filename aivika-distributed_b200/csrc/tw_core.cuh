@@ -145,6 +145,7 @@ struct alignas(16) Ctl {         // device-resident control block
                        c_sent_local, c_sent_remote, c_fossil, c_long, c_steps;   // order == enum in engine.cu
     double   gvt_cap;            // GlobalTimeMessage of an external Time Server: gvt never exceeds it (+inf = none)
     unsigned long long c_skipped; // host-injected messages older than GVT that were skipped (dioAllowSkippingOutdatedMessage)
+    uint32_t max_occ, pad1;       // most ring slots any LP of this partition had in use at the start of a super-step
     unsigned long long c_rounds;  // closed-group kernel: rounds of the slowest warp, summed over launches
 };
 
@@ -153,11 +154,12 @@ struct Acc {
     double pend_min, emit_min;
     uint32_t exec, rb_events, rollbacks, strag, anti, annih, retry, sent_local, sent_remote, fossil;
     uint32_t long_lanes;             // LPs that started the step with more than 8 * kMaskBits pending entries
+    uint32_t max_occ;                // most ring slots in use by an LP of this thread (retained entries + arrivals)
     uint32_t err, err_lp;
     TW_HD void init()
     {
         pend_min = pos_inf(); emit_min = pos_inf();
-        exec = rb_events = rollbacks = strag = anti = annih = retry = sent_local = sent_remote = fossil = long_lanes = 0;
+        exec = rb_events = rollbacks = strag = anti = annih = retry = sent_local = sent_remote = fossil = long_lanes = max_occ = 0;
         err = 0; err_lp = 0;
     }
     TW_HD void fail(uint32_t code, uint32_t lp) { if (!err) { err = code; err_lp = lp; } }
@@ -166,6 +168,7 @@ struct Acc {
         pend_min = dmin(pend_min, o.pend_min); emit_min = dmin(emit_min, o.emit_min);
         exec += o.exec; rb_events += o.rb_events; rollbacks += o.rollbacks; strag += o.strag; anti += o.anti; annih += o.annih;
         retry += o.retry; sent_local += o.sent_local; sent_remote += o.sent_remote; fossil += o.fossil; long_lanes += o.long_lanes;
+        max_occ = o.max_occ > max_occ ? o.max_occ : max_occ;
         if (!err && o.err) { err = o.err; err_lp = o.err_lp; }
     }
 };
@@ -950,7 +953,10 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     const bool bulk = kBulk && TW_SIMT && heavy && !exact_only;
     // (tells the host which build of k_step to launch next: a few dozen entries over the list's reach -- a c4 run has some
     // hundred such LPs in every step -- are handled well enough by the per-event search; hundreds of entries are not)
-    if (live && nreg > 8u * kMaskBits) acc.long_lanes++;
+    if (live && nreg > 8u * kMaskBits) {
+        acc.long_lanes++;
+        acc.max_occ = consumed - head > acc.max_occ ? consumed - head : acc.max_occ;   // (only worth tracking where rings fill up)
+    }
     bool exact_once = false;                                 // bulk lane: the front of the region is tied, one exact search
     double bulk_rest = pos_inf();                            // bulk lane: lower bound of what the last selection left behind
     double rest_min = pos_inf();

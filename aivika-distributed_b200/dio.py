@@ -311,6 +311,12 @@ class DIO:
         self._check(self.lib.tw_skipped_outdated(self.h, C.byref(n)))
         return n.value
 
+    def maxRingOccupancy(self):
+        """Largest number of ring slots an LP with a long pending region had in use (0: no such LP); see tw_max_ring_occupancy."""
+        n = C.c_uint32()
+        self._check(self.lib.tw_max_ring_occupancy(self.h, C.byref(n)))
+        return n.value
+
     def globalTimeMessage(self, t):
         """GlobalTimeMessage t -> updateGlobalTime; returns False when the value was ignored (above the local time)."""
         ok = C.c_int()

@@ -265,6 +265,7 @@ def main():
             assert int(n_exec.sum()) == int(st.committed)
             digests.append(W.lp_digest(dio.lp_base, n_exec, h))
     launches = lib.tw_kernel_launch_count() - launches0
+    max_occ = dio.maxRingOccupancy()
     # the same end-to-end step with the start-time events created on the device (tw_populate: every LP's own
     # runEventInStartTime), i.e. without shipping the synthetic population over PCIe -- reported beside `e2e`, not instead
     e2e_dev_s = []
@@ -290,6 +291,7 @@ def main():
 
     # max over ranks of the per-step device time, sum over ranks of the committed events
     _, e2e_dev_l, _ = D.reduce_run(dist, world, dev_ms, e2e_dev_s, [0], device="cuda")
+    occ_l, _, _ = D.reduce_run(dist, world, [float(max_occ)], [0.0], [0], device="cuda")     # MAX over ranks
     ms_l, e2e_l, cnt = D.reduce_run(dist, world, dev_ms, e2e_s,
                                     [committed[0], stats[-1]["executed"], stats[-1]["rolled_back"], stats[-1]["anti_sent"],
                                      stats[-1]["sent_remote"], stats[-1]["sent_local"], launches,
@@ -351,6 +353,9 @@ def main():
             "committed_events_per_step": tot_committed, "executed_events_per_step": tot_exec,
             "rollback_efficiency": tot_committed / max(1, tot_exec),
             "rolled_back_per_step": tot_rb, "anti_messages_per_step": tot_anti,
+            "anti_messages_per_sec": tot_anti * K / (total_ms / 1e3),
+            "max_ring_occupancy": {"slots": int(occ_l[0]), "queue_capacity": wl["cap"],
+                                   "note": "largest ring fill of an LP with more than 256 pending events (0: none had)"},
             "remote_messages_per_step": tot_remote, "local_messages_per_step": tot_local,
             "supersteps_per_step": steps_per_run, "trace_hash_sum": hex(trace_hash_total), "lp_digest": hex(lp_digest_total),
             "parity": parity,

@@ -241,6 +241,10 @@ int tw_global_time_message(tw_engine *e, double global_time, int *accepted);
 
 /* Messages dropped under TW_FLAG_SKIP_OUTDATED since tw_create / tw_reset (logOutdatedMessage, Internal/Event.hs:372). */
 int tw_skipped_outdated(tw_engine *e, uint64_t *count);
+/* Largest number of ring slots (retained entries + arrivals) an LP with a long pending region (> 256 entries: the hot LPs
+ * of a skewed workload) had in use since tw_create / tw_reset; 0 when no LP ever held that many.  The fixed ring is this
+ * engine's form of the memory thresholds of isEventOverflow (Internal/Event.hs:289-306): compare with queue_capacity. */
+int tw_max_ring_occupancy(tw_engine *e, uint32_t *slots);
 
 /* Partition geometry: first global LP id and LP count owned by this rank. */
 int tw_partition(const tw_engine *e, uint32_t *lp_base, uint32_t *n_local);
