@@ -168,7 +168,7 @@ __device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, ui
             ctl->pend_min = ordered_bits(pos_inf());
             ctl->emit_min = ordered_bits(pos_inf());
             ctl->step = step + 1; ctl->c_steps += 1;
-            ctl->done_blocks = 0; ctl->tile_next = 0;
+            ctl->done_blocks = 0; ctl->tile_next = 0; ctl->hot_cnt[step & 1u] = 0;    // (this step's list is used up)
             __threadfence();
         }
         __syncwarp();
@@ -203,13 +203,37 @@ __global__ void __launch_bounds__(kBlock, TW_MINBLOCKS) k_step(const __grid_cons
         // block finishes.  The next assignment is requested before the current tiles are run, so its round trip is hidden.
         // The work queue is carried from tile to tile.
         const uint32_t n_tiles = (d.n_local + 31u) >> 5;
+        // (the build with the bulk selection also runs the tiles that held a long pending region in the previous step FIRST:
+        // a hot LP's tile takes ten to twenty times longer than an ordinary one, and met late in the tile order it alone
+        // would be the step's tail.  Such tiles register themselves for the next step in hot_list; the ordinary pass skips them.)
+        const bool hot_first = kBulk && d.tiles == 1u && !(d.flags & kFlagNoHotFirst);
+        const uint32_t hc = hot_first ? __ldcg(&ctl->hot_cnt[step & 1u]) : 0u;
+        const uint32_t n_virtual = n_tiles + hc;
         const uint32_t first_dyn = gridDim.x * (kBlock / 32) * d.tiles;        // tiles beyond the statically assigned ones
         uint32_t tile0 = (blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * d.tiles;
-        while (tile0 < n_tiles) {
+        while (tile0 < n_virtual) {
             uint32_t next = 0xFFFFFFFFu;
-            if (first_dyn < n_tiles && (threadIdx.x & 31u) == 0u) next = first_dyn + atomicAdd(&ctl->tile_next, d.tiles);
-            for (uint32_t t = 0; t < d.tiles; ++t)
-                lp_step<M, kBulk>(d, acc, q, (tile0 + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+            if (first_dyn < n_virtual && (threadIdx.x & 31u) == 0u) next = first_dyn + atomicAdd(&ctl->tile_next, d.tiles);
+            uint32_t tile = tile0; bool skip = false;
+            if constexpr (kBulk) {
+                if (hc) {
+                    if (tile0 < hc) tile = __ldcg(&d.hot_list[(size_t)(step & 1u) * n_tiles + tile0]);
+                    else { tile = tile0 - hc; skip = __ldcg(&d.hot_mark[(size_t)(step & 1u) * n_tiles + tile]) == step; }
+                }
+            }
+            if (!skip) {
+                const uint32_t long0 = acc.long_lanes;
+                for (uint32_t t = 0; t < d.tiles; ++t)
+                    lp_step<M, kBulk>(d, acc, q, (tile + t) * 32u + (threadIdx.x & 31u), gvt, wend, step);   // all lanes enter: phases reconverge inside
+                if constexpr (kBulk) {
+                    const bool lng = __any_sync(0xffffffffu, acc.long_lanes != long0);
+                    if (lng && hot_first && (threadIdx.x & 31u) == 0u) {
+                        const uint32_t idx = atomicAdd(&ctl->hot_cnt[(step + 1u) & 1u], 1u);
+                        d.hot_list[(size_t)((step + 1u) & 1u) * n_tiles + idx] = tile;
+                        d.hot_mark[(size_t)((step + 1u) & 1u) * n_tiles + tile] = step + 1u;    // (per parity: this step's marks are still being read)
+                    }
+                }
+            }
             tile0 = __shfl_sync(0xffffffffu, next, 0);
         }
         q.drain(d, acc, step & 1u);
@@ -404,7 +428,8 @@ __global__ void __launch_bounds__(kBlock) k_init(const Dev<M> d, double start_ti
     const uint32_t l = blockIdx.x * kBlock + threadIdx.x;
     if (l == 0) {
         // the step counter is never rewound: it tags the cross-GPU GVT mailboxes, and a tag must not repeat across runs
-        const uint32_t next_step = (d.ctl->step + 2u) & ~1u;
+        // (+4: a tile registered as hot for the step after the last one of the previous run must not match a step of this run)
+        const uint32_t next_step = (d.ctl->step + 4u) & ~1u;
         Ctl c; memset(&c, 0, sizeof c);
         c.step = next_step;
         c.gvt = start_time; c.gvt_local = start_time;
@@ -649,6 +674,7 @@ struct Engine : EngineBase {
         d.horizon = (p.time_horizon >= 0.0) ? p.time_horizon : -1.0;     // NaN compares false -> unbounded
         d.mp = M::make_params(p);
         d.flags = p.flags & 0xFFFFu;
+        if (const char *e = getenv("TWB200_HOT_FIRST")) { if (!atoi(e)) d.flags |= kFlagNoHotFirst; }
         if (const char *e = getenv("TWB200_FENCE")) { if (!strcmp(e, "gpu")) d.flags |= kFlagFenceGpu; else if (!strcmp(e, "none")) d.flags |= kFlagFenceNone; }
         {
             double ms = p.sync_timeout_ms ? (double)p.sync_timeout_ms : 20000.0;   // a peer that stays away this long is gone
@@ -672,6 +698,12 @@ struct Engine : EngineBase {
         d.in = (LPIn *)meta; d.hdr = (LPHdr *)((char *)meta + off_hdr); d.state = (typename M::State *)((char *)meta + off_state);
         TW_CUDA(cudaMalloc(&d.ctl, sizeof(Ctl)));
         TW_CUDA(cudaMemset(d.ctl, 0, sizeof(Ctl)));
+        {
+            const size_t nt = (nl + 31) / 32;
+            TW_CUDA(cudaMalloc(&d.hot_list, 2 * nt * sizeof(uint32_t)));
+            TW_CUDA(cudaMalloc(&d.hot_mark, 2 * nt * sizeof(uint32_t)));
+            TW_CUDA(cudaMemset(d.hot_mark, 0, 2 * nt * sizeof(uint32_t)));   // step numbers start at 2: nothing is marked
+        }
         TW_CUDA(cudaMalloc(&d.stage_cnt, kMaxWorld * kCntStride * sizeof(uint32_t)));
         TW_CUDA(cudaMemset(d.stage_cnt, 0, kMaxWorld * kCntStride * sizeof(uint32_t)));
         // Closed groups (replicas): a warp iterates the super-steps of its groups inside one launch (k_run_groups).  A round
@@ -1134,7 +1166,7 @@ struct Engine : EngineBase {
         if (comm) g_nccl.CommDestroy(comm);
         cudaFree(d.pages); cudaFree(d.saved); cudaFree(meta); cudaFree(d.ctl);
         cudaFree(d_stage); cudaFree(d_tmp); cudaFree(d_stats); cudaFree(d_slots); cudaFree(d_peer_slots);
-        cudaFree(d.stage_cnt); cudaFree(d.stage_in); cudaFree(d.grp_gvt);
+        cudaFree(d.stage_cnt); cudaFree(d.stage_in); cudaFree(d.grp_gvt); cudaFree(d.hot_list); cudaFree(d.hot_mark);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
         if (ev_chk[0]) cudaEventDestroy(ev_chk[0]); if (ev_chk[1]) cudaEventDestroy(ev_chk[1]);

@@ -146,6 +146,7 @@ struct alignas(16) Ctl {         // device-resident control block
     double   gvt_cap;            // GlobalTimeMessage of an external Time Server: gvt never exceeds it (+inf = none)
     unsigned long long c_skipped; // host-injected messages older than GVT that were skipped (dioAllowSkippingOutdatedMessage)
     uint32_t max_occ, pad1;       // most ring slots any LP of this partition had in use at the start of a super-step
+    uint32_t hot_cnt[2];          // tiles with a long pending region, registered for the step of that parity (run first)
     unsigned long long c_rounds;  // closed-group kernel: rounds of the slowest warp, summed over launches
 };
 
@@ -178,6 +179,7 @@ constexpr uint32_t kFlagSkipOutdated = 1u;   // tw_params.flags bit 0: dioAllowS
 constexpr uint32_t kFlagNoGroupKernel = 2u;  // tw_params.flags bit 1: run closed-group models through k_step as well
 constexpr uint32_t kFlagFenceGpu = 1u << 16; // engine-internal (TWB200_FENCE=gpu|none): scope of the per-thread fence after a
 constexpr uint32_t kFlagFenceNone = 1u << 17; // multi-GPU super-step's peer stores (default: system)
+constexpr uint32_t kFlagNoHotFirst = 1u << 18; // engine-internal (TWB200_HOT_FIRST=0): tiles in index order in every build
 
 template <class M>
 struct Dev {                     // passed to kernels by value
@@ -204,6 +206,8 @@ struct Dev {                     // passed to kernels by value
     uint32_t           stage_cap;
     GvtSlot           *peer_slots[kMaxWorld];   // every rank's GVT mailbox: slots[parity][sender rank]
     unsigned long long *grp_gvt;                // closed-group kernel: ordered bits of every group's own GVT
+    uint32_t *hot_list;                         // [2][tiles]: tiles to run first in the step of that parity (longest work first)
+    uint32_t *hot_mark;                         // [2][tiles]: the step a tile is registered for, by that step's parity
     unsigned long long peer_timeout_ns;         // wall-clock bound of the cross-GPU mailbox wait (a lost peer becomes an error)
 };
 
@@ -708,9 +712,26 @@ TW_NOINLINE uint32_t coop_select(typename M::Event *lpg, uint32_t mask, uint32_t
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(0xffffffffu, oow, o); oow = t < oow ? t : oow; }
     // the exact prefix: below the bound, and no two neighbours (nor the last one and the bound) in one time quantum
+    // One kind of tie is harmless and common: an annihilated message and its anti-message, both waiting to be skipped as
+    // no-ops, have the very same receive time.  A run of neighbours in one quantum may stay in the prefix if ALL of them
+    // are annihilated and equal in time; any other run ends the prefix where it starts (an entry of the same quantum with an
+    // earlier exact time may sit anywhere inside it).
     const unsigned long long nxt = __shfl_sync(0xffffffffu, best, (int)((lane + 1u) & 31u));
-    const unsigned long long after = lane == 31u ? bound : (nxt < bound ? nxt : bound);     // the smallest key behind this one
-    const bool ok = best != kNone && lane < want && best < bound && (best >> 32) != (after >> 32);
+    uint64_t my_ctr = 0; double my_ts = 0.0;
+    if (best != kNone) { const Event *pe = lpg + ((beg + (uint32_t)best) & mask); my_ctr = pe->ctr; my_ts = pe->recv_ts; }
+    const bool dead = (my_ctr & kDeadBit) != 0ull;
+    const bool nxt_dead = __shfl_sync(0xffffffffu, (int)dead, (int)((lane + 1u) & 31u)) != 0;
+    const double nxt_ts = __shfl_sync(0xffffffffu, my_ts, (int)((lane + 1u) & 31u));
+    const bool same_next = lane < 31u && best != kNone && nxt != kNone && (best >> 32) == (nxt >> 32);
+    const bool bad_next = same_next && !(dead && nxt_dead && my_ts == nxt_ts);
+    const unsigned samem = __ballot_sync(0xffffffffu, same_next), badm = __ballot_sync(0xffffffffu, bad_next);
+    uint32_t run_limit = 32u;                                   // first lane of the first run that holds a bad pair
+    if (badm) {
+        const uint32_t f = (uint32_t)__ffs((int)badm) - 1u;
+        const unsigned zeros = ~samem & ((1u << f) - 1u);       // lanes below f that do not continue into their neighbour
+        run_limit = bitlen64((uint64_t)zeros);
+    }
+    const bool ok = best != kNone && lane < want && lane < run_limit && best < bound && (best >> 32) != (bound >> 32);
     const unsigned okm = __ballot_sync(0xffffffffu, ok);
     const uint32_t m = okm == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okm) - 1u;          // leading run of ok lanes
     // what stays pending behind the prefix: the next key (or the bound), and the records beyond the window

@@ -227,6 +227,19 @@ def test_warp_level_paths_machrep(H, horizon, batch):
     assert rc == 0 and all(r1[r].up_time_prop == mr[r].up_time_prop for r in range(3))
 
 
+def test_bulk_selection_with_equal_time_runs(H):
+    """The cooperative bulk selection (coop_select) on a model whose messages come in runs of one receive time: MachRep2 with
+    unbounded optimism and a large batch lets the master hold far more than 32 pending events, many of them annihilated
+    pairs.  Regression: a run of one time quantum may only stay in the selected prefix when ALL of it is annihilated and
+    equal in time -- a pairwise check let an earlier live event of the same quantum be executed after a later no-op
+    (TW_ERR_TIME_ORDER on the GPU and here)."""
+    p = H.machrep_params(512, 3.0, horizon=-1.0, batch=16, cap=1024)      # (the pairwise check failed at LP 717 in step 17)
+    res = H.oracle_machrep(p)
+    rc, n_exec, h, mr, stats = H.emu_simt_run(p, 1, 1, 1)
+    assert rc == 0 and stats.rolled_back > 0
+    assert all(res[r].up_time_prop == mr[r].up_time_prop and res[r].immed_prop == mr[r].immed_prop for r in range(512))
+
+
 # ---------------------------------------------------------------- closed groups: the warp-local super-step loop (k_run_groups)
 @pytest.mark.parametrize("horizon,batch,gpw,budget,every", [(-1.0, 4, 2, 64, 1), (2.0, 4, 10, 8, 1), (0.0, 1, 1, 2, 1), (-1.0, 16, 3, 1000, 3),
                                                             (5.0, 8, 4, 2, 7)])

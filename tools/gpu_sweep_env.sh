@@ -5,7 +5,7 @@ mkdir -p $OUT
 : > $OUT/${TAG}_sweep.txt
 while IFS='|' read -r envspec bargs; do
   [ -z "$bargs" ] && continue
-  env $envspec python bench.py $bargs --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | python -c "
+  env $envspec timeout 300 python bench.py $bargs --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 ok = False
 for l in sys.stdin:
