@@ -636,6 +636,17 @@ __device__ __forceinline__ void coop_min(const typename M::Event *lpg, uint32_t 
     ix_out = __shfl_sync(0xffffffffu, bix, w2 ? __ffs((int)w2) - 1 : 0);    // identical keys (twins): any of them
 }
 
+// broadcast a plain struct from one lane of the warp (32 bits at a time)
+template <class T>
+__device__ __forceinline__ T shfl_pod(const T &v, int src)
+{
+    static_assert(sizeof(T) % 4 == 0, "shfl_pod moves 32-bit words");
+    T r; const uint32_t *in = reinterpret_cast<const uint32_t *>(&v); uint32_t *out = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 4; ++i) out[i] = __shfl_sync(0xffffffffu, in[i], src);
+    return r;
+}
+
 // Cooperative bulk selection for a long pending region (hot LPs of a skewed workload hold a thousand pending events and
 // execute dozens of them per super-step; one whole-region search per event made that quadratic).  The warp selects up to
 // `want` (<= 32) of the earliest in-window records of the leader's region in ONE pass and moves them, in order, to the
@@ -1069,8 +1080,47 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             const uint64_t lg = __shfl_sync(0xffffffffu, (unsigned long long)gbits, leader), ll = __shfl_sync(0xffffffffu, (unsigned long long)lbits, leader);
             double rest_; bool left_;
             const uint32_t m = coop_select<M>(lpg, mask, lbeg, ln, lg, ll, lwant, rest_, left_);
+            // A model whose transition cannot fail and needs no saved state (split + reversible: PHOLD) has its lined-up
+            // records executed right here by the whole warp: lane j fetches record j (one coalesced load), every lane runs
+            // the leader's short sequential chain of state transitions (same instructions on all lanes, record k comes by
+            // shuffle from lane k) and keeps the state before ITS record, and then all lanes queue their Work items at once
+            // -- instead of one warp-wide loop iteration per event with a single busy lane.
+            uint32_t m_exec = 0; bool thr = false;
+            if constexpr (M::kSplit && M::kReversible) {
+                if (m) {
+                    const uint32_t lane = threadIdx.x & 31u;
+                    const uint32_t llp = __shfl_sync(0xffffffffu, lp, leader);
+                    State cs = shfl_pod(st, leader);
+                    double clvt = __shfl_sync(0xffffffffu, h.lvt, leader);
+                    uint32_t cnproc = __shfl_sync(0xffffffffu, nproc, leader);
+                    const double lgvt = __shfl_sync(0xffffffffu, gvt, leader);
+                    Event e; e.recv_ts = 0.0; e.ctr = 0;
+                    if (lane < m) e = lpg[(lbeg + lane) & mask];
+                    State pre = cs; bool bad_order = false;
+                    for (uint32_t k = 0; k < m; ++k) {
+                        const Event ek = shfl_pod(e, (int)k);
+                        if (ek.recv_ts < clvt) { bad_order = true; break; }
+                        if (cnproc >= d.proc_limit && !(ek.recv_ts <= lgvt)) { thr = true; break; }   // isEventOverflow analogue
+                        if (lane == k) pre = cs;
+                        if (!(ek.ctr & (kAntiBit | kDeadBit))) M::advance(d.mp, llp, cs, ek);
+                        clvt = ek.recv_ts; ++cnproc; ++m_exec;
+                    }
+                    const bool mine = lane < m_exec;
+                    const bool noop = (e.ctr & (kAntiBit | kDeadBit)) != 0ull;
+                    if (mine && noop && !(e.ctr & kNoopBit)) lpg[(lbeg + lane) & mask].ctr = e.ctr | kNoopBit;
+                    Work w;
+                    const bool has = mine && !noop;
+                    if (has) { w = M::make_work(llp, pre, e, false); acc.exec++; }
+                    q.push(d, acc, parity, has, w);
+                    if ((int)lane == leader) {
+                        st = cs; h.lvt = clvt; nproc = cnproc; done += m_exec;
+                        if (bad_order) { fail_checked<M>(d, acc, TW_ERR_TIME_ORDER, l, head_prev); live = false; stopped = true; searched = true; }
+                        if (thr) stopped = true;
+                    }
+                }
+            }
             if ((int)(threadIdx.x & 31u) == leader) {
-                presel = m; bulk_rest = rest_;
+                presel = m - m_exec; bulk_rest = rest_;
                 if (m == 0u) {
                     if (left_ && !(rest_ > limit)) exact_once = true;            // a tie at the front: settle one event exactly
                     else { rest_min = dmin(rest_min, rest_); searched = true; }  // nothing (more) inside the window
