@@ -147,6 +147,9 @@ struct alignas(16) Ctl {         // device-resident control block
     unsigned long long c_skipped; // host-injected messages older than GVT that were skipped (dioAllowSkippingOutdatedMessage)
     uint32_t max_occ, pad1;       // most ring slots any LP of this partition had in use at the start of a super-step
     uint32_t hot_cnt[2];          // tiles with a long pending region, registered for the step of that parity (run first)
+#ifdef TW_PHASE_TIMERS
+    unsigned long long t_phase[8];
+#endif
     unsigned long long c_rounds;  // closed-group kernel: rounds of the slowest warp, summed over launches
 };
 
@@ -308,6 +311,16 @@ TW_HD uint32_t bitlen64(uint64_t m) { return m ? 64u - (uint32_t)__builtin_clzll
 #define TW_NOINLINE
 TW_HD bool warp_any(bool p) { return p; }
 TW_HD uint32_t bitlen64(uint64_t m) { return m ? 64u - (uint32_t)__builtin_clzll(m) : 0u; }
+#endif
+
+// Diagnostic build (-DTW_PHASE_TIMERS): SM clock cycles a lane with a long pending region spends in each phase of its
+// super-step, summed into Ctl::t_phase (printed by tw_run); compiled out otherwise.
+#if defined(TW_PHASE_TIMERS) && defined(__CUDA_ARCH__)
+#define TW_T0() long long tw_t_ = clock64(); const bool tw_hot_ = live && (hdr_consumed_guess > 256u)
+#define TW_TICK(i) do { if (tw_hot_) { const long long n_ = clock64(); atomicAdd(&d.ctl->t_phase[i], (unsigned long long)(n_ - tw_t_)); tw_t_ = n_; } } while (0)
+#else
+#define TW_T0() ((void)0)
+#define TW_TICK(i) ((void)0)
 #endif
 
 // ------------------------------------------------------------------ the work queue of a warp
@@ -636,6 +649,62 @@ __device__ __forceinline__ void coop_min(const typename M::Event *lpg, uint32_t 
     ix_out = __shfl_sync(0xffffffffu, bix, w2 ? __ffs((int)w2) - 1 : 0);    // identical keys (twins): any of them
 }
 
+// The slow path of the inbox drain (drain_slow) run by the whole warp for an LP with a long ring: the case analysis is
+// the same, arrival by arrival, but the twin of an anti-message is looked for by all 32 lanes, 128 records per round trip,
+// newest first -- on a hot LP of a skewed workload one lane's search through a thousand records was the longest thing a
+// super-step had to wait for.  All lanes call it with the leader's arguments and compute the same results.
+template <class M>
+__device__ __forceinline__ void drain_slow_coop(typename M::Event *pg, uint32_t mask, uint32_t head, uint32_t nproc, uint32_t consumed0,
+                                                uint32_t consumed, double lvt, uint32_t &rb_out, uint32_t &annih_out, uint32_t &strag_out,
+                                                bool &unmatched)
+{
+    using Event = typename M::Event;
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    uint32_t rb = nproc, annih = 0, strag = 0;
+    unmatched = false;
+    for (uint32_t a = consumed0; a != consumed; ++a) {
+        const Event e = pg[a & mask];                           // (the same record on every lane)
+        if (e.ctr & kAntiBit) {
+            // the positive twin among what arrived in EARLIER super-steps (see drain_slow), newest first
+            uint32_t found = kNone;
+            for (uint32_t top = consumed0; top != head && found == kNone; ) {
+                const uint32_t span = top - head < 128u ? top - head : 128u;
+                double ts[4];
+#pragma unroll
+                for (uint32_t u = 0; u < 4u; ++u) {
+                    const uint32_t off = u * 32u + lane;
+                    ts[u] = off < span ? pg[(top - 1u - off) & mask].recv_ts : neg_inf();
+                }
+                uint32_t my = kNone;                            // the newest match among this lane's four records
+#pragma unroll
+                for (uint32_t u = 0; u < 4u; ++u) {
+                    const uint32_t off = u * 32u + lane;
+                    if (my != kNone || off >= span || ts[u] != e.recv_ts) continue;
+                    const Event m = pg[(top - 1u - off) & mask];
+                    if (!(m.ctr & (kAntiBit | kDeadBit)) && same_message(m, e)) my = off;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const uint32_t t = __shfl_xor_sync(0xffffffffu, my, o); my = t < my ? t : my; }
+                if (my != kNone) found = top - 1u - my;
+                top -= span;
+            }
+            if (found == kNone) { unmatched = true; break; }
+            const uint32_t rel = found - head;
+            if (rel < rb) rb = rel;                             // twin already processed: roll back including it
+            if (lane == 0u) { pg[found & mask].ctr |= kDeadBit; pg[a & mask].ctr = e.ctr | kDeadBit; }
+            __syncwarp();
+            annih++;
+        } else if (nproc > 0 && !(e.recv_ts > lvt)) {
+            // possible straggler: walk back over processed entries whose key is greater
+            uint32_t r = rb < nproc ? rb : nproc;
+            while (r > 0 && key_less(e, pg[(head + r - 1) & mask])) --r;
+            if (r < nproc) { if (r < rb) rb = r; strag++; }
+        }
+    }
+    rb_out = rb; annih_out = annih; strag_out = strag;
+}
+
 // broadcast a plain struct from one lane of the warp (32 bits at a time)
 template <class T>
 __device__ __forceinline__ T shfl_pod(const T &v, int src)
@@ -825,6 +894,8 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     }
     if (live) st = d.state[l];
 
+    const uint32_t hdr_consumed_guess = consumed - head; (void)hdr_consumed_guess;
+    TW_T0();
     // ---- 1. lazy fossil collection, strict `< gvt`: four independent probes at the quartiles of the processed region
     // (Every fourth step unless the processed region is about to throttle optimism: the probes are cold DRAM reads
     // that the whole warp waits for, so the lanes of a warp had better take them in the same step.)
@@ -844,6 +915,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     }
     TW_RECONVERGE();
 
+    TW_TICK(0);
     // ---- 2. drain the inbox, fast path: arrivals are the last narr entries of the region.  Anything that
     // needs the processed region (anti-message, possible straggler) takes the slow path.
     bool slow = false;
@@ -865,7 +937,25 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
         }
         if (!live) slow = false;
     }
+    TW_TICK(1);
     uint32_t rb = nproc;                                         // processed position to roll back to (nproc = none)
+#if TW_SIMT
+    if constexpr (kBulk) {
+        // an LP with a long ring: the slow path runs with all 32 lanes (drain_slow_coop)
+        for (unsigned sm = __ballot_sync(0xffffffffu, slow && consumed0 - head > 8u * kMaskBits); sm; sm &= sm - 1u) {
+            const int leader = __ffs(sm) - 1;
+            Event *lpg = reinterpret_cast<Event *>(__shfl_sync(0xffffffffu, (unsigned long long)pg, leader));
+            uint32_t rb_ = 0, annih_ = 0, strag_ = 0; bool unm_ = false;
+            drain_slow_coop<M>(lpg, mask, __shfl_sync(0xffffffffu, head, leader), __shfl_sync(0xffffffffu, nproc, leader),
+                               __shfl_sync(0xffffffffu, consumed0, leader), __shfl_sync(0xffffffffu, consumed, leader),
+                               __shfl_sync(0xffffffffu, h.lvt, leader), rb_, annih_, strag_, unm_);
+            if ((int)(threadIdx.x & 31u) == leader) {
+                rb = rb_; acc.annih += annih_; acc.strag += strag_; slow = false;
+                if (unm_) { fail_checked<M>(d, acc, TW_ERR_ANTI_UNMATCHED, l, head_prev); live = false; }
+            }
+        }
+    }
+#endif
     if (slow) {
         StepCtx<M> c;                                            // lives in local memory only on this rare path
         c.lvt = h.lvt; c.head_prev = head_prev; c.head = head; c.nproc = nproc; c.consumed0 = consumed0; c.consumed = consumed; c.rb = nproc; c.live = live;
@@ -876,6 +966,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     }
     TW_RECONVERGE();
 
+    TW_TICK(2);
     // ---- 3. rollback to processed position rb: restore the saved state (rollbackLog, Internal/UndoableLog.hs:93-118),
     // un-process the inputs (rollbackInputMessages, Internal/InputMessageQueue.hs:190-201) and queue the anti-messages
     // of the undone executions, regenerated from the saved pre-states.  Warp-uniform loop: one undone entry per lane
@@ -949,6 +1040,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
         // many pending events --, and the pass reads every pending record: every 16th step, and at once above seven
         // eighths.  Not rarer: tombstones that stay are "executed" as no-ops and use up the LP's batch -- c5 needed 576
         // instead of 545 super-steps with the pass only above three quarters)
+        TW_TICK(3);
         if (live && consumed - head >= (d.cap >> 1) && ((step & 15u) == 0u || consumed - head >= d.cap - (d.cap >> 3))) {
             Acc sacc; sacc.init();
             head = compact_slow<M>(d, sacc, l, head, nproc, consumed);
@@ -957,6 +1049,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
     }
     TW_RECONVERGE();
 
+    TW_TICK(4);
     // ---- 4./5. select and execute in key order, at most max_batch events.
     // Selection (light lanes: regions of at most kMaskBits entries, non-negative times): ONE pass over the pending
     // region sorts the entries inside the optimistic window by a packed 32-bit key -- the receive time quantised to 27
@@ -1226,6 +1319,7 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
         // the list is used up but more in-window entries were seen: next round
         need_scan = !heavy && !stopped && done < maxb && c[0] == kNoCand && nleft > 0;
     }
+    TW_TICK(5);
     // what stays pending inside the window (batch limit, retry, throttle) still bounds GVT: the earliest such entry
     if (live && !heavy && nleft > 0) {
         if (c[0] != kNoCand) {                               // the list's head is its exact minimum (ties were ruled out)
