@@ -1059,8 +1059,8 @@ struct Engine : EngineBase {
         if (result == TW_OK) result = check_device_error(c);
         if (monitor) monitor_flush();
 #ifdef TW_PHASE_TIMERS
-        fprintf(stderr, "[twb200 phase timers, cycles of lanes with > 256 ring entries] fossil %llu drain %llu drain_slow %llu rollback %llu compact %llu select+execute %llu | long lane-steps %llu\n",
-                c.t_phase[0], c.t_phase[1], c.t_phase[2], c.t_phase[3], c.t_phase[4], c.t_phase[5], c.c_long);
+        fprintf(stderr, "[twb200 phase timers, cycles of lanes with > 256 ring entries] fossil %llu drain %llu drain_slow %llu rollback %llu compact %llu select+execute %llu | selections %llu selected %llu | long lane-steps %llu\n",
+                c.t_phase[0], c.t_phase[1], c.t_phase[2], c.t_phase[3], c.t_phase[4], c.t_phase[5], c.t_phase[6], c.t_phase[7], c.c_long);
 #endif
         if (st) {
             memset(st, 0, sizeof *st);

@@ -741,15 +741,15 @@ TW_NOINLINE uint32_t coop_select(typename M::Event *lpg, uint32_t mask, uint32_t
     { const uint64_t R = lbits - gbits; const uint32_t len = bitlen64(R); qs = len > 32u ? len - 32u : 0u; if ((R >> qs) >= 0xFFFFFFFFull) ++qs; }
     unsigned long long c0 = kNone, c1 = kNone, c2 = kNone, c3 = kNone, bound = kNone;   // this lane's four smallest keys; smallest dropped
     uint64_t oow = ~0ull;                                       // earliest record beyond the window (exact bits)
-    for (uint32_t k = lane; k < n; k += 128u) {
-        uint64_t tb[4];
+    for (uint32_t k = lane; k < n; k += 256u) {                 // (eight loads in flight per lane: the pass is latency-bound)
+        uint64_t tb[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const uint32_t kk = k + 32u * (uint32_t)u;
             tb[u] = kk < n ? d2bits(lpg[(beg + kk) & mask].recv_ts) : ~0ull;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const uint32_t kk = k + 32u * (uint32_t)u;
             const bool in = tb[u] <= lbits;
             oow = (!in && tb[u] < oow) ? tb[u] : oow;
@@ -793,24 +793,28 @@ TW_NOINLINE uint32_t coop_select(typename M::Event *lpg, uint32_t mask, uint32_t
     for (int o = 16; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(0xffffffffu, oow, o); oow = t < oow ? t : oow; }
     // the exact prefix: below the bound, and no two neighbours (nor the last one and the bound) in one time quantum
     // One kind of tie is harmless and common: an annihilated message and its anti-message, both waiting to be skipped as
-    // no-ops, have the very same receive time.  A run of neighbours in one quantum may stay in the prefix if ALL of them
-    // are annihilated and equal in time; any other run ends the prefix where it starts (an entry of the same quantum with an
-    // earlier exact time may sit anywhere inside it).
+    // no-ops, have the very same receive time -- and so has the copy the rolled-back sender sent again (a deterministic
+    // model re-executes the same event).  A run of neighbours in one quantum may stay in the prefix if ALL of them are
+    // equal in time and AT MOST ONE of them is not annihilated (no-ops commute with everything); any other run ends the
+    // prefix where it starts (an entry of the same quantum with an earlier exact time may sit anywhere inside it).
     const unsigned long long nxt = __shfl_sync(0xffffffffu, best, (int)((lane + 1u) & 31u));
     uint64_t my_ctr = 0; double my_ts = 0.0;
     if (best != kNone) { const Event *pe = lpg + ((beg + (uint32_t)best) & mask); my_ctr = pe->ctr; my_ts = pe->recv_ts; }
     const bool dead = (my_ctr & kDeadBit) != 0ull;
-    const bool nxt_dead = __shfl_sync(0xffffffffu, (int)dead, (int)((lane + 1u) & 31u)) != 0;
     const double nxt_ts = __shfl_sync(0xffffffffu, my_ts, (int)((lane + 1u) & 31u));
     const bool same_next = lane < 31u && best != kNone && nxt != kNone && (best >> 32) == (nxt >> 32);
-    const bool bad_next = same_next && !(dead && nxt_dead && my_ts == nxt_ts);
-    const unsigned samem = __ballot_sync(0xffffffffu, same_next), badm = __ballot_sync(0xffffffffu, bad_next);
-    uint32_t run_limit = 32u;                                   // first lane of the first run that holds a bad pair
-    if (badm) {
-        const uint32_t f = (uint32_t)__ffs((int)badm) - 1u;
-        const unsigned zeros = ~samem & ((1u << f) - 1u);       // lanes below f that do not continue into their neighbour
-        run_limit = bitlen64((uint64_t)zeros);
-    }
+    const unsigned samem = __ballot_sync(0xffffffffu, same_next);
+    const unsigned diffm = __ballot_sync(0xffffffffu, same_next && my_ts != nxt_ts);     // one quantum, two times
+    const unsigned livem = __ballot_sync(0xffffffffu, best != kNone && !dead);
+    // this lane's run: lanes [run_s, run_e], linked by set bits of samem
+    const unsigned below = ~samem & ((1u << lane) - 1u);
+    const uint32_t run_s = bitlen64((uint64_t)below);
+    const unsigned above = ~samem >> lane;                      // (bit 31 of samem is never set, so `above` is never 0)
+    const uint32_t run_e = lane + (uint32_t)__ffs((int)above) - 1u;
+    const unsigned runm = (run_e >= 31u ? 0xFFFFFFFFu : ((1u << (run_e + 1u)) - 1u)) & ~((1u << run_s) - 1u);
+    const bool bad_run = run_e > run_s && ((diffm & runm & ~(1u << run_e)) != 0u || __popc(livem & runm) > 1);
+    const unsigned badrm = __ballot_sync(0xffffffffu, bad_run);
+    const uint32_t run_limit = badrm ? (uint32_t)__ffs((int)badrm) - 1u : 32u;             // first lane of the first bad run
     const bool ok = best != kNone && lane < want && lane < run_limit && best < bound && (best >> 32) != (bound >> 32);
     const unsigned okm = __ballot_sync(0xffffffffu, ok);
     const uint32_t m = okm == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~okm) - 1u;          // leading run of ok lanes
@@ -1173,6 +1177,9 @@ TW_HD void lp_step(const Dev<M> &d, Acc &acc, WorkQ<M> &q, uint32_t l, double gv
             const uint64_t lg = __shfl_sync(0xffffffffu, (unsigned long long)gbits, leader), ll = __shfl_sync(0xffffffffu, (unsigned long long)lbits, leader);
             double rest_; bool left_;
             const uint32_t m = coop_select<M>(lpg, mask, lbeg, ln, lg, ll, lwant, rest_, left_);
+#if defined(TW_PHASE_TIMERS) && defined(__CUDA_ARCH__)
+            if ((int)(threadIdx.x & 31u) == leader) { atomicAdd(&d.ctl->t_phase[6], 1ull); atomicAdd(&d.ctl->t_phase[7], (unsigned long long)m); }
+#endif
             // A model whose transition cannot fail and needs no saved state (split + reversible: PHOLD) has its lined-up
             // records executed right here by the whole warp: lane j fetches record j (one coalesced load), every lane runs
             // the leader's short sequential chain of state transitions (same instructions on all lanes, record k comes by
