@@ -7,8 +7,9 @@ A "step" is one complete run of the synthetic workload (load the start-time mess
 the stop time, read the per-LP results).  `value` is device-timed (CUDA events inside tw_run, inputs resident in
 HBM); `e2e` is the same metric through the public API with HOST buffers (pinned host -> device copy of the
 start-time messages and device -> host read of the per-LP results inside the timed region).
-For N > 1 launch with torchrun: one rank per GPU, the LP range is sharded, messages to remote LPs are NVLink
-peer atomics + stores from inside the step kernel and GVT is a peer-memory mailbox round run by its last block.
+For N > 1 launch with torchrun: one rank per GPU, the LP range is sharded, messages to remote LPs are NVLink peer
+stores from inside the step kernel into staging rings in the receiver's memory (no atomic crosses NVLink; the receiver
+routes them with k_deliver) and GVT is a peer-memory mailbox round run by the step kernel's last block.
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/, kind "port"; the Haskell engine
 itself cannot be built in this image: no GHC) on a bounded sample of the same workload.

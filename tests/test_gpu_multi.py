@@ -1,6 +1,6 @@
 """Multi-GPU parity (needs >= 2 B200s on one box: `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi`).
-One process per GPU (torchrun), LP ranges sharded, remote messages as NVLink peer stores + peer atomics from inside
-k_step, GVT by the peer-memory mailbox round of its last block.  The gathered per-LP committed counts / trace hashes must equal the CPU oracle's,
+One process per GPU (torchrun), LP ranges sharded, remote messages as NVLink peer stores from inside k_step into
+per-sender staging rings of the receiver (routed by k_deliver), GVT by the peer-memory mailbox round of its last block.  The gathered per-LP committed counts / trace hashes must equal the CPU oracle's,
 i.e. the committed trace is identical for every number of GPUs."""
 import os
 import subprocess
