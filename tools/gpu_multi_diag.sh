@@ -1,8 +1,8 @@
 # Round 2, multi-GPU call: staging-ring exchange against the oracle (tools/multi_rank_check.py), scaling bench line of c4,
-# the same without remote messages, per-kernel timing.  usage: bash tools/gpu_r2j.sh N TAG
+# the same without remote messages, per-kernel timing.  usage: gpurun --gpus N -- bash tools/gpu_multi_diag.sh N TAG
 set -x
 N=${1:-2}
-TAG=${2:-r2j}
+TAG=${2:-multi}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi topo -m > $OUT/${TAG}_topo_n$N.txt 2>&1
