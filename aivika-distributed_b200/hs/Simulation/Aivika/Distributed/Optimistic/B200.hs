@@ -69,6 +69,8 @@ foreign import ccall safe "tw_enqueue_message"  c_tw_enqueue_message  :: Ptr () 
 foreign import ccall safe "tw_enqueue_messages" c_tw_enqueue_messages :: Ptr () -> Ptr () -> CSize -> IO CInt
 -- | runEventInStartTime of every LP on the device (the model's own start-time events; no host buffer).
 foreign import ccall safe "tw_populate" c_tw_populate :: Ptr () -> IO CInt
+-- | Largest ring fill of an LP with a long pending region (the fixed-capacity form of the isEventOverflow thresholds).
+foreign import ccall safe "tw_max_ring_occupancy" c_tw_max_ring_occupancy :: Ptr () -> Ptr Word32 -> IO CInt
 foreign import ccall safe "tw_run"     c_tw_run     :: Ptr () -> CDouble -> Ptr () -> IO CInt
 foreign import ccall safe "tw_gvt"     c_tw_gvt     :: Ptr () -> Ptr CDouble -> IO CInt
 foreign import ccall safe "tw_read_machrep" c_tw_read_machrep :: Ptr () -> Ptr () -> CSize -> IO CInt
