@@ -227,6 +227,20 @@ def test_warp_level_paths_machrep(H, horizon, batch):
     assert rc == 0 and all(r1[r].up_time_prop == mr[r].up_time_prop for r in range(3))
 
 
+def test_hot_lp_cooperative_paths(H):
+    """One LP receives most of the traffic and holds ~1000 pending events (the shape of C5's hot LPs): the warp-level build
+    takes the cooperative bulk selection (coop_select), executes the lined-up records with the whole warp and runs the slow
+    path of the inbox drain -- anti-messages, stragglers -- with all 32 lanes (drain_slow_coop, rings of more than 256
+    entries).  The committed trace must equal the sequential oracle's for several shuffles and batch sizes."""
+    for batch, seed in ((64, 5), (16, 6), (3, 7)):
+        p = H.phold_params(256, 2.0, population=8, remote_pct=80, n_hot=1, hot_pct=80, horizon=1.0, cap=4096, batch=batch,
+                           proc_limit=1024)
+        o_exec, o_hash, o_sum = H.oracle_phold(p)
+        rc, e_exec, e_hash, _, stats = H.emu_simt_run(p, seed, 1, 1)
+        assert rc == 0 and (e_exec == o_exec).all() and (e_hash == o_hash).all()
+        assert stats.rolled_back > 0 and stats.annihilated > 0 and int(o_exec[0]) > 1000      # the hot LP really was hot
+
+
 def test_bulk_selection_with_equal_time_runs(H):
     """The cooperative bulk selection (coop_select) on a model whose messages come in runs of one receive time: MachRep2 with
     unbounded optimism and a large batch lets the master hold far more than 32 pending events, many of them annihilated
