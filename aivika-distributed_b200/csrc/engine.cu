@@ -113,7 +113,12 @@ __device__ __forceinline__ void gvt_exchange_warp(Ctl *ctl, GvtSlot *const *peer
     const unsigned long long m = warp_min_u64(ordered_bits(v));
     if (r == 0) {
         if (bad) { if (atomicCAS(&ctl->error, 0u, bad) == 0u) ctl->err_lp = 0xFFFFFFFFu; }
-        else { const double g = from_ordered(m), cap = *(volatile double *)&ctl->gvt_cap; ctl->gvt = g < cap ? g : cap; }
+        else {
+            double g = from_ordered(m);
+            const double cap = *(volatile double *)&ctl->gvt_cap, prev = *(volatile double *)&ctl->gvt;
+            g = g < cap ? g : cap;
+            ctl->gvt = g < prev ? prev : g;          // the global time never goes back (see block_finish)
+        }
     }
 }
 
@@ -163,6 +168,13 @@ __device__ __forceinline__ void block_finish(const Dev<M> &d, const Acc &acc, ui
             const unsigned long long pm = *(volatile unsigned long long *)&ctl->pend_min;
             const unsigned long long em = *(volatile unsigned long long *)&ctl->emit_min;
             g = from_ordered(pm < em ? pm : em);
+            // What an LP leaves pending is sometimes reported as the lower bound of a time quantum of the current window
+            // (tw_core.cuh: `drop`, coop_select's `rest`).  Under an external Time Server the window's base lags behind, and
+            // such a bound can lie a fraction of a quantum below what the partition reported a step earlier: the local
+            // time handed out never goes back (the previous value is itself a lower bound of everything still unprocessed).
+            // (One partition: its local time IS the global one.  Several: only the global minimum is monotone -- a peer may
+            // send this partition a message below its last local minimum --, so the clamp sits in gvt_exchange_warp.)
+            if (d.world == 1) { const double prev = *(volatile double *)&ctl->gvt_local; if (g < prev) g = prev; }
             ctl->gvt_local = g;
             if (d.world == 1) { const double cap = *(volatile double *)&ctl->gvt_cap; ctl->gvt = g < cap ? g : cap; }   // otherwise the cross-GPU minimum follows
             ctl->pend_min = ordered_bits(pos_inf());

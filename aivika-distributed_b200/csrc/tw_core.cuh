@@ -793,10 +793,12 @@ TW_NOINLINE uint32_t coop_select(typename M::Event *lpg, uint32_t mask, uint32_t
     for (int o = 16; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(0xffffffffu, oow, o); oow = t < oow ? t : oow; }
     // the exact prefix: below the bound, and no two neighbours (nor the last one and the bound) in one time quantum
     // One kind of tie is harmless and common: an annihilated message and its anti-message, both waiting to be skipped as
-    // no-ops, have the very same receive time -- and so has the copy the rolled-back sender sent again (a deterministic
-    // model re-executes the same event).  A run of neighbours in one quantum may stay in the prefix if ALL of them are
-    // equal in time and AT MOST ONE of them is not annihilated (no-ops commute with everything); any other run ends the
-    // prefix where it starts (an entry of the same quantum with an earlier exact time may sit anywhere inside it).
+    // no-ops, have the very same receive time.  A run of neighbours in one quantum may stay in the prefix if ALL of them
+    // are equal in time and ALL are annihilated: their mutual order is irrelevant.  Any other run ends the prefix where it
+    // starts: an entry of the same quantum with an earlier exact time may sit anywhere inside it, and even one live record
+    // among no-ops of its own time must not be misplaced -- the processed region has to stay sorted by the full key among
+    // live records, or the straggler test (which walks back until it meets a smaller key) would stop at a no-op in front of
+    // a live record it ought to roll back (found by the warp-level emulator on a workload where every time is tied).
     const unsigned long long nxt = __shfl_sync(0xffffffffu, best, (int)((lane + 1u) & 31u));
     uint64_t my_ctr = 0; double my_ts = 0.0;
     if (best != kNone) { const Event *pe = lpg + ((beg + (uint32_t)best) & mask); my_ctr = pe->ctr; my_ts = pe->recv_ts; }
@@ -812,7 +814,7 @@ TW_NOINLINE uint32_t coop_select(typename M::Event *lpg, uint32_t mask, uint32_t
     const unsigned above = ~samem >> lane;                      // (bit 31 of samem is never set, so `above` is never 0)
     const uint32_t run_e = lane + (uint32_t)__ffs((int)above) - 1u;
     const unsigned runm = (run_e >= 31u ? 0xFFFFFFFFu : ((1u << (run_e + 1u)) - 1u)) & ~((1u << run_s) - 1u);
-    const bool bad_run = run_e > run_s && ((diffm & runm & ~(1u << run_e)) != 0u || __popc(livem & runm) > 1);
+    const bool bad_run = run_e > run_s && ((diffm & runm & ~(1u << run_e)) != 0u || (livem & runm) != 0u);
     const unsigned badrm = __ballot_sync(0xffffffffu, bad_run);
     const uint32_t run_limit = badrm ? (uint32_t)__ffs((int)badrm) - 1u : 32u;             // first lane of the first bad run
     const bool ok = best != kNone && lane < want && lane < run_limit && best < bound && (best >> 32) != (bound >> 32);

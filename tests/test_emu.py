@@ -241,6 +241,29 @@ def test_hot_lp_cooperative_paths(H):
         assert stats.rolled_back > 0 and stats.annihilated > 0 and int(o_exec[0]) > 1000      # the hot LP really was hot
 
 
+def test_bulk_selection_keeps_the_processed_region_sorted_when_every_time_is_tied(H):
+    """Regression (found by tools/stress_emu.py on the warp-level build): with mean 0 every delay equals the lookahead, so
+    all receive times are tied.  A selection that let ONE live record stay among annihilated records of its own time could
+    line it up behind a no-op with a smaller key; the straggler test then stopped at the no-op and missed a rollback
+    (wrong committed trace, no error).  Only runs that are annihilated throughout may stay in a selected prefix."""
+    p = H.phold_params(214, 2.0, population=7, remote_pct=30, lookahead=0.1, mean=0.0, seed=1915008829, n_hot=16, hot_pct=30,
+                       horizon=0.3, cap=512, batch=4, world=2, fossil=2)
+    o_exec, o_hash, _ = H.oracle_phold(p)
+    rc, e_exec, e_hash, _, _ = H.emu_simt_run(p, 0, 1, 1)         # (shuffles 0, 1, 2, 4 and 7 of 8 failed before the fix)
+    assert rc == 0 and (e_exec == o_exec).all() and (e_hash == o_hash).all()
+
+
+def test_local_time_never_goes_back_under_a_lagging_time_server(H):
+    """Regression (same stress run): what a long pending region leaves behind is reported as the lower bound of a time
+    quantum of the current window; with GVT refreshed only every 5th step (an external Time Server) that bound could lie
+    a hair below the previous step's local time.  The engine publishes the running maximum (block_finish)."""
+    p = H.machrep_params(10, 40.0, horizon=50.0, cap=256, batch=4, seed1=211992, seed2=247124)
+    res = H.oracle_machrep(p)
+    for sd in (0, 1, 3):
+        rc, n_exec, h, mr, _ = H.emu_simt_run(p, sd, 5, 1)
+        assert rc == 0 and all(res[r].up_time_prop == mr[r].up_time_prop for r in range(10))
+
+
 def test_bulk_selection_with_equal_time_runs(H):
     """The cooperative bulk selection (coop_select) on a model whose messages come in runs of one receive time: MachRep2 with
     unbounded optimism and a large batch lets the master hold far more than 32 pending events, many of them annihilated
